@@ -1,0 +1,118 @@
+/* kzg.h -- C ABI of the B200-native Zstandard decompressor ("Kompressor zstd on GPU").
+ *
+ * This is the drop-in boundary for Kompressor's zstd decode path.  Plain C: pointers and sizes only.
+ * Three layers:
+ *
+ *  Layer A  batch API -- the measured path.  Independent frames decoded as one GPU batch.
+ *  Layer B  streaming shim with libzstd semantics under the kzg_ prefix.  One-for-one replacements of
+ *           the six libzstd functions the reference binds for decompression:
+ *             ZSTD_createDCtx           <- Wrapper.cpp:128, ZstdDecompressor.native.kt:32
+ *             ZSTD_freeDCtx             <- Wrapper.cpp:139, ZstdDecompressor.native.kt:37
+ *             ZSTD_DCtx_loadDictionary  <- Wrapper.cpp:70,  ZstdDecompressor.native.kt:42
+ *             ZSTD_decompressStream     <- Wrapper.cpp:178, ZstdDecompressor.native.kt:62-66
+ *             ZSTD_isError              <- Wrapper.cpp:192, ZstdDecompressor.native.kt:69
+ *             ZSTD_getErrorName         <- Wrapper.cpp:195, ZstdDecompressor.native.kt:70
+ *           (paths relative to kompressor-zstd--nativelib/src/{jvmCommonMain/jni,nativeMain/kotlin/...}).
+ *           The kzg_ prefix is required because the compressor side keeps using the real libzstd in
+ *           the same process.
+ *  Layer C  JNI symbols Java_com_ensody_kompressor_zstd_ZstdWrapper_* (kzg_jni.cpp), compiled only
+ *           where <jni.h> exists; see INTEGRATION.md.
+ *
+ * There is no CPU fallback: every entry point that decodes requires a CUDA device and fails with
+ * an error if none is usable.
+ */
+#ifndef KZG_H
+#define KZG_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KZG_VERSION_STRING "0.1.0"
+
+/* Error convention: identical to libzstd's.  Functions returning size_t return (size_t)-code on
+ * error; kzg_isError(r) is r > (size_t)-120.  Codes are libzstd 1.5.7's ZSTD_ErrorCode values, which
+ * is what Kompressor's checkErrorResult prints
+ * (kompressor-zstd--nativelib/src/jvmCommonMain/kotlin/com/ensody/kompressor/zstd/ZstdCompressor.jvm.kt:45-51). */
+unsigned kzg_isError(size_t code);
+const char* kzg_getErrorName(size_t code);
+const char* kzg_versionString(void);
+
+/* ------------------------------------------------------------------ Layer A: batch API */
+typedef struct kzg_ctx kzg_ctx;
+
+/* Creates a decode context on CUDA device `device` (-1 = current device). Returns 0 on success,
+ * otherwise a positive ZSTD_ErrorCode (64 = allocation / no usable device). */
+int kzg_ctx_create(kzg_ctx** out, int device);
+void kzg_ctx_destroy(kzg_ctx* ctx);
+
+/* Frame table builder (host). Walks concatenated zstd / skippable frames in [buf, buf+len) using only
+ * frame and block headers and records up to max_frames entries:
+ *   off[i], size[i]   position and compressed size of frame i
+ *   content[i]        Frame_Content_Size if present, else an upper bound (n_blocks * block_max);
+ *                     0 for skippable frames
+ * *consumed = bytes covered by complete frames.  Stops without error at a truncated frame.
+ * Returns the number of frames, or (size_t)-code (for example unknown magic -> -10). */
+size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, uint64_t* size, uint64_t* content,
+                       size_t max_frames, size_t* consumed);
+
+/* Decodes n_frames independent frames whose bytes are already in device memory.
+ *   d_src + d_src_off[i], d_src_size[i]   exactly one zstd (or skippable) frame each
+ *   d_dst + d_dst_off[i], d_dst_cap[i]    where its output goes and how much room there is
+ *   d_status[i]                           out: 0 or ZSTD_ErrorCode (20 corruption, 22 checksum, 70 dst too small...)
+ *   d_out_size[i]                         out: decoded bytes
+ * All pointers are device pointers; the 16-byte aligned chunks around every byte of d_src must be
+ * readable (true for any cudaMalloc allocation).  total_src_bytes / total_dst_cap / max_frame_dst_cap
+ * are host-side sums / max of the table, used to size the workspace.  Work is enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream) and NOT synchronised.
+ * Returns the number of kernels launched (> 0), or a negative ZSTD_ErrorCode. */
+int kzg_decompress_batch_device(kzg_ctx* ctx, const void* d_src, const uint64_t* d_src_off,
+                                const uint64_t* d_src_size, void* d_dst, const uint64_t* d_dst_off,
+                                const uint64_t* d_dst_cap, uint64_t n_frames, uint64_t total_src_bytes,
+                                uint64_t total_dst_cap, uint64_t max_frame_dst_cap, uint32_t* d_status,
+                                uint64_t* d_out_size, void* cuda_stream);
+
+/* Synchronises the stream used by the last kzg_decompress_batch_device call and reports whether the
+ * workspace was too small (optimistic sizing).  Returns 0 = results valid, 1 = workspace has been
+ * grown: enqueue the same batch again, negative = CUDA failure. */
+int kzg_batch_finish(kzg_ctx* ctx);
+
+/* Same batch, host memory: copies the frames to the device, decodes, copies output, status and
+ * sizes back (synchronous; retries internally if the workspace had to grow).  Pinned host memory
+ * (kzg_host_alloc) makes the copies asynchronous and full-speed.  Returns 0 or a negative code. */
+int kzg_decompress_batch_host(kzg_ctx* ctx, const void* src, const uint64_t* src_off, const uint64_t* src_size,
+                              void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n_frames,
+                              uint32_t* status, uint64_t* out_size);
+
+void* kzg_host_alloc(size_t bytes);   /* pinned host memory */
+void kzg_host_free(void* p);
+
+/* Statistics of the last batch (for bench.py): kernels launched, workspace bytes, device time is
+ * measured by the caller with CUDA events. */
+typedef struct {
+    uint32_t n_blocks, n_cblocks, n_hblocks, n_sblocks;
+    uint64_t lit_bytes, seq_records, workspace_bytes;
+    uint32_t launches, tile_bytes, sm_count, overflow;
+} kzg_batch_stats;
+int kzg_last_batch_stats(kzg_ctx* ctx, kzg_batch_stats* out);
+
+/* ------------------------------------------------------------------ Layer B: streaming shim */
+typedef struct kzg_DCtx kzg_DCtx;
+typedef struct { const void* src; size_t size; size_t pos; } kzg_inBuffer;   /* == ZSTD_inBuffer */
+typedef struct { void* dst; size_t size; size_t pos; } kzg_outBuffer;        /* == ZSTD_outBuffer */
+
+kzg_DCtx* kzg_createDCtx(void);                                               /* NULL if no GPU */
+size_t kzg_freeDCtx(kzg_DCtx* dctx);
+size_t kzg_DCtx_loadDictionary(kzg_DCtx* dctx, const void* dict, size_t dictSize);
+/* Returns 0 when a frame is completely decoded and flushed, a positive hint when more input or
+ * output room is needed, or an error.  Always consumes all offered input (Kompressor never sets
+ * input.insufficient for zstd) and keeps returning non-zero while it still holds undelivered output,
+ * which is what `output.insufficient = output.isFull && result != 0` needs
+ * (ZstdDecompressor.jvm.kt:38, ZstdDecompressor.native.kt:72). */
+size_t kzg_decompressStream(kzg_DCtx* dctx, kzg_outBuffer* output, kzg_inBuffer* input);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,356 @@
+// C ABI, layer A (batch API): context, workspace, frame-table builder.  See include/kzg.h.
+#include "../../include/kzg.h"
+#include "kzg_kernels.cuh"
+#include "kzg_parse.cuh"
+#include "kzg_entropy.cuh"
+
+#include <mutex>
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "kzg: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -(int)KZG_E_MEMORY; } } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct kzg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::mutex mu;
+    DevBuf frames, blocks, cblocks, fse, huf, hlist, slist, lit, seq, ctr, consts;
+    // sizing state (sticky across batches, grown on overflow)
+    u64 block_cap = 0, cblock_cap = 0, lit_cap = 0, seq_cap = 0;
+    u32 tile_bytes = 0;
+    double lit_factor = 0.75, seq_div = 12.0, block_div = 32768.0;
+    KzgCounters* h_ctr = nullptr;   // pinned
+    cudaStream_t last_stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    u32 last_launches = 0;
+    u64 last_n_frames = 0;
+    // staging for the host-pointer form
+    DevBuf st_src, st_dst, st_tab;
+};
+
+static const char* err_name(u32 c) {
+    switch (c) {
+        case 0: return "No error detected";
+        case 1: return "Error (generic)";
+        case 10: return "Unknown frame descriptor";
+        case 12: return "Version not supported";
+        case 14: return "Unsupported frame parameter";
+        case 16: return "Frame requires too much memory for decoding";
+        case 20: return "Data corruption detected";
+        case 22: return "Restored data doesn't match checksum";
+        case 24: return "Header of Literals' block doesn't respect format specification";
+        case 30: return "Dictionary is corrupted";
+        case 32: return "Dictionary mismatch";
+        case 34: return "Cannot create Dictionary from provided samples";
+        case 40: return "Unsupported parameter";
+        case 41: return "Unsupported combination of parameters";
+        case 42: return "Parameter is out of bound";
+        case 44: return "tableLog requires too much memory : unsupported";
+        case 46: return "Unsupported max Symbol Value : too large";
+        case 48: return "Specified maxSymbolValue is too small";
+        case 50: return "pledged buffer stability condition is not respected";
+        case 60: return "Operation not authorized at current processing stage";
+        case 62: return "Context should be init first";
+        case 64: return "Allocation error : not enough memory";
+        case 66: return "workSpace buffer is not large enough";
+        case 70: return "Destination buffer is too small";
+        case 72: return "Src size is incorrect";
+        case 74: return "Operation on NULL destination buffer";
+        case 80: return "Operation made no progress over multiple calls, due to output buffer being full";
+        case 82: return "Operation made no progress over multiple calls, due to input being empty";
+        case 100: return "Frame index is too large";
+        case 102: return "An I/O error occurred when reading/seeking";
+        case 104: return "Destination buffer is wrong";
+        case 105: return "Source buffer is wrong";
+        case 106: return "Block-level external sequence producer returned an error code";
+        case 107: return "External sequences are not valid";
+        default: return "Unspecified error code";
+    }
+}
+
+extern "C" unsigned kzg_isError(size_t code) { return code > (size_t)0 - (size_t)120; }
+extern "C" const char* kzg_getErrorName(size_t code) { return kzg_isError(code) ? err_name((u32)((size_t)0 - code)) : err_name(0); }
+extern "C" const char* kzg_versionString(void) { return KZG_VERSION_STRING; }
+
+extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
+    if (!out) return (int)KZG_E_GENERIC;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fprintf(stderr, "kzg: no CUDA device available; this library has no CPU fallback\n");
+        return (int)KZG_E_MEMORY;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return (int)KZG_E_MEMORY; }
+    if (device >= ndev) return (int)KZG_E_MEMORY;
+    if (cudaSetDevice(device) != cudaSuccess) return (int)KZG_E_MEMORY;
+    kzg_ctx* c = new (std::nothrow) kzg_ctx();
+    if (!c) return (int)KZG_E_MEMORY;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) fprintf(stderr, "kzg: warning: built for sm_100a, device is sm_%d%d\n", prop.major, prop.minor);
+    if (cudaMallocHost((void**)&c->h_ctr, sizeof(KzgCounters)) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
+    memset(c->h_ctr, 0, sizeof(KzgCounters));
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFreeHost(c->h_ctr); delete c; return (int)KZG_E_MEMORY; }
+    // constants: default FSE descriptor + packed code tables
+    struct { KzgFseDesc d; u32 codes[96]; } hc;
+    memset(&hc, 0, sizeof hc);
+    kzg_default_fse_desc(hc.d);
+    kzg_code_tables(hc.codes, hc.codes + 36);
+    if (c->consts.ensure(sizeof hc) || c->ctr.ensure(sizeof(KzgCounters)) ||
+        cudaMemcpy(c->consts.p, &hc, sizeof hc, cudaMemcpyHostToDevice) != cudaSuccess) {
+        kzg_ctx_destroy(c);
+        return (int)KZG_E_MEMORY;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf* all[] = { &c->frames, &c->blocks, &c->cblocks, &c->fse, &c->huf, &c->hlist, &c->slist, &c->lit, &c->seq,
+                      &c->ctr, &c->consts, &c->st_src, &c->st_dst, &c->st_tab };
+    for (DevBuf* b : all) b->release();
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" void* kzg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void kzg_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, uint64_t* size, uint64_t* content,
+                                  size_t max_frames, size_t* consumed) {
+    const u8* p = (const u8*)buf;
+    size_t pos = 0, n = 0;
+    if (consumed) *consumed = 0;
+    while (pos < len && n < max_frames) {
+        const u8* f = p + pos;
+        const size_t rem = len - pos;
+        if (rem < 4) break;
+        const u32 magic = kzg_rd32(f);
+        if ((magic & 0xFFFFFFF0u) == KZG_SKIP_MAGIC) {
+            if (rem < 8) break;
+            const u64 fs = 8ull + kzg_rd32(f + 4);
+            if (fs > rem) break;
+            if (off) off[n] = pos;
+            if (size) size[n] = fs;
+            if (content) content[n] = 0;
+            n++; pos += (size_t)fs;
+            if (consumed) *consumed = pos;
+            continue;
+        }
+        if (magic != KZG_MAGIC) return (size_t)0 - (size_t)KZG_E_PREFIX_UNKNOWN;
+        KzgFrameHeader h;
+        const u32 e = kzg_parse_frame_header(f, rem, h);
+        if (e == KZG_E_SRCSIZE_WRONG) break;
+        if (e) return (size_t)0 - (size_t)e;
+        const u64 bmax = h.window_size < KZG_BLOCK_MAX ? h.window_size : KZG_BLOCK_MAX;
+        u64 q = h.hdr_size, bound = 0;
+        bool complete = false;
+        for (;;) {
+            if (q + 3 > rem) break;
+            const u32 bh = kzg_rd24(f + q);
+            const u32 type = (bh >> 1) & 3, bsz = bh >> 3;
+            if (type == 3) return (size_t)0 - (size_t)KZG_E_CORRUPTION;
+            const u64 adv = type == 1 ? 1 : bsz;
+            if (q + 3 + adv > rem) break;
+            bound += type == 2 ? bmax : bsz;
+            q += 3 + adv;
+            if (bh & 1) { complete = true; break; }
+        }
+        if (!complete) break;
+        if (h.has_checksum) { if (q + 4 > rem) break; q += 4; }
+        if (off) off[n] = pos;
+        if (size) size[n] = q;
+        if (content) content[n] = h.fcs != ~0ull ? h.fcs : bound;
+        n++; pos += (size_t)q;
+        if (consumed) *consumed = pos;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int ensure_workspace(kzg_ctx* c, u64 n_frames, u64 total_src, u64 total_dst, u64 max_frame_dst) {
+    u64 want_blocks = n_frames + (u64)((double)total_dst / c->block_div) + 64;
+    if (want_blocks > 0xFFFFFFF0ull) want_blocks = 0xFFFFFFF0ull;
+    if (want_blocks > c->block_cap) { c->block_cap = want_blocks; c->cblock_cap = want_blocks; }
+    const u64 want_lit = (u64)((double)total_dst * c->lit_factor) + n_frames * 48 + (1u << 16);
+    if (want_lit > c->lit_cap) c->lit_cap = want_lit;
+    const u64 want_seq = (u64)((double)total_dst / c->seq_div) + n_frames * 8 + (1u << 12);
+    if (want_seq > c->seq_cap) c->seq_cap = want_seq;
+    u64 blk = max_frame_dst < KZG_BLOCK_MAX ? max_frame_dst : KZG_BLOCK_MAX;
+    u32 tile = (u32)((blk + 15) & ~15ull) + 64;
+    if (tile < 16384 + 64) tile = 16384 + 64;
+    if (tile > c->tile_bytes) c->tile_bytes = tile;
+    (void)total_src;
+    if (c->frames.ensure(n_frames * sizeof(KzgFrame)) || c->blocks.ensure(c->block_cap * sizeof(KzgBlock)) ||
+        c->cblocks.ensure(c->cblock_cap * sizeof(KzgCBlock)) || c->fse.ensure(c->cblock_cap * sizeof(KzgFseDesc)) ||
+        c->huf.ensure(c->cblock_cap * sizeof(KzgHufDesc)) || c->hlist.ensure(c->cblock_cap * 4) ||
+        c->slist.ensure(c->cblock_cap * 4) || c->lit.ensure(c->lit_cap + 64) || c->seq.ensure(c->seq_cap * 8))
+        return -1;
+    return 0;
+}
+
+extern "C" int kzg_decompress_batch_device(kzg_ctx* c, const void* d_src, const uint64_t* d_src_off,
+                                           const uint64_t* d_src_size, void* d_dst, const uint64_t* d_dst_off,
+                                           const uint64_t* d_dst_cap, uint64_t n_frames, uint64_t total_src_bytes,
+                                           uint64_t total_dst_cap, uint64_t max_frame_dst_cap, uint32_t* d_status,
+                                           uint64_t* d_out_size, void* cuda_stream) {
+    if (!c) return -(int)KZG_E_GENERIC;
+    if (n_frames > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    c->last_stream = stream;
+    c->last_n_frames = n_frames;
+    c->last_launches = 0;
+    if (n_frames == 0) return 0;
+    if (ensure_workspace(c, n_frames, total_src_bytes, total_dst_cap, max_frame_dst_cap)) return -(int)KZG_E_MEMORY;
+    KzgBatch b;
+    memset(&b, 0, sizeof b);
+    b.src = (const u8*)d_src; b.src_off = d_src_off; b.src_size = d_src_size;
+    b.dst = (u8*)d_dst; b.dst_off = d_dst_off; b.dst_cap = d_dst_cap;
+    b.status = d_status; b.out_size = d_out_size;
+    b.n_frames = (u32)n_frames;
+    b.tile_bytes = c->tile_bytes;
+    b.frames = (KzgFrame*)c->frames.p; b.blocks = (KzgBlock*)c->blocks.p; b.cblocks = (KzgCBlock*)c->cblocks.p;
+    b.fse = (KzgFseDesc*)c->fse.p; b.huf = (KzgHufDesc*)c->huf.p;
+    b.hlist = (u32*)c->hlist.p; b.slist = (u32*)c->slist.p;
+    b.lit_pool = (u8*)c->lit.p; b.seq_pool = (u64*)c->seq.p;
+    b.ctr = (KzgCounters*)c->ctr.p;
+    b.fse_default = (const KzgFseDesc*)c->consts.p;
+    b.code_tables = (const u32*)((const u8*)c->consts.p + sizeof(KzgFseDesc));
+    b.lit_cap = c->lit_cap; b.seq_cap = c->seq_cap;
+    b.block_cap = (u32)c->block_cap; b.cblock_cap = (u32)c->cblock_cap;
+    b.dict = nullptr; b.dict_size = 0; b.dict_id = 0;
+    CK(cudaMemsetAsync(c->ctr.p, 0, sizeof(KzgCounters), stream));
+    const int launches = kzg_launch_batch(b, c->sm_count, stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(KzgCounters), cudaMemcpyDeviceToHost, stream));
+    c->last_launches = (u32)launches;
+    return launches;
+}
+
+extern "C" int kzg_batch_finish(kzg_ctx* c) {
+    if (!c) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->last_stream));
+    if (c->last_n_frames == 0) return 0;
+    const KzgCounters& k = *c->h_ctr;
+    if (!k.overflow) return 0;
+    if (k.overflow & 3u) {
+        const u64 need = (u64)(k.n_blocks > k.n_cblocks ? k.n_blocks : k.n_cblocks) + 64;
+        c->block_cap = c->cblock_cap = need > c->block_cap * 2 ? need : c->block_cap * 2;
+    }
+    if (k.overflow & 4u) c->lit_cap = k.lit_used + (k.lit_used >> 4) + 4096;
+    if (k.overflow & 8u) c->seq_cap = k.seq_used + (k.seq_used >> 4) + 4096;
+    if (k.overflow & 16u) c->tile_bytes = KZG_BLOCK_MAX + 64;
+    return 1;
+}
+
+extern "C" int kzg_last_batch_stats(kzg_ctx* c, kzg_batch_stats* out) {
+    if (!c || !out) return -(int)KZG_E_GENERIC;
+    const KzgCounters& k = *c->h_ctr;
+    out->n_blocks = k.n_blocks; out->n_cblocks = k.n_cblocks; out->n_hblocks = k.n_hblocks; out->n_sblocks = k.n_sblocks;
+    out->lit_bytes = k.lit_used; out->seq_records = k.seq_used;
+    out->workspace_bytes = c->frames.cap + c->blocks.cap + c->cblocks.cap + c->fse.cap + c->huf.cap + c->hlist.cap +
+                           c->slist.cap + c->lit.cap + c->seq.cap;
+    out->launches = c->last_launches; out->tile_bytes = c->tile_bytes; out->sm_count = (u32)c->sm_count;
+    out->overflow = k.overflow;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint64_t* src_off, const uint64_t* src_size,
+                                         void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n,
+                                         uint32_t* status, uint64_t* out_size) {
+    if (!c) return -(int)KZG_E_GENERIC;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    // extent of the source / destination spans and sizing sums
+    u64 src_lo = ~0ull, src_hi = 0, dst_lo = ~0ull, dst_hi = 0, tot_src = 0, tot_dst = 0, max_dst = 0;
+    for (u64 i = 0; i < n; i++) {
+        if (src_off[i] < src_lo) src_lo = src_off[i];
+        if (src_off[i] + src_size[i] > src_hi) src_hi = src_off[i] + src_size[i];
+        if (dst_off[i] < dst_lo) dst_lo = dst_off[i];
+        if (dst_off[i] + dst_cap[i] > dst_hi) dst_hi = dst_off[i] + dst_cap[i];
+        tot_src += src_size[i]; tot_dst += dst_cap[i];
+        if (dst_cap[i] > max_dst) max_dst = dst_cap[i];
+    }
+    const u64 src_span = src_hi - src_lo, dst_span = dst_hi - dst_lo;
+    // device staging: [src span | pad], [dst span], tables: off/size/doff/dcap (u64 each) + out_size (u64) + status (u32)
+    const u64 tab_bytes = n * (5 * 8 + 4);
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        if (c->st_src.ensure(src_span + 64) || c->st_dst.ensure(dst_span + 64) || c->st_tab.ensure(tab_bytes + 64))
+            return -(int)KZG_E_MEMORY;
+    }
+    cudaStream_t s = c->own_stream;
+    u64* t_off = (u64*)c->st_tab.p;
+    u64* t_size = t_off + n;
+    u64* t_doff = t_size + n;
+    u64* t_dcap = t_doff + n;
+    u64* t_osize = t_dcap + n;
+    u32* t_status = (u32*)(t_osize + n);
+    // rebased offset tables
+    u64* h_tab = (u64*)malloc(n * 4 * 8);
+    if (!h_tab) return -(int)KZG_E_MEMORY;
+    for (u64 i = 0; i < n; i++) {
+        h_tab[i] = src_off[i] - src_lo; h_tab[n + i] = src_size[i];
+        h_tab[2 * n + i] = dst_off[i] - dst_lo; h_tab[3 * n + i] = dst_cap[i];
+    }
+    int rc = 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        if (cudaMemcpyAsync(c->st_tab.p, h_tab, n * 4 * 8, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            cudaMemcpyAsync(c->st_src.p, (const u8*)src + src_lo, src_span, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = -(int)KZG_E_MEMORY; break; }
+        rc = kzg_decompress_batch_device(c, c->st_src.p, t_off, t_size, c->st_dst.p, t_doff, t_dcap, n, tot_src, tot_dst,
+                                         max_dst, t_status, t_osize, s);
+        if (rc < 0) break;
+        rc = kzg_batch_finish(c);
+        if (rc <= 0) break;
+    }
+    if (rc == 1) rc = -(int)KZG_E_MEMORY;
+    if (rc == 0) {
+        bool ok = cudaMemcpyAsync(status, t_status, n * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                  cudaMemcpyAsync(out_size, t_osize, n * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+        // copy back only the caller's capacity regions, coalescing adjacent ones into runs
+        u64 run_lo = dst_off[0], run_hi = dst_off[0] + dst_cap[0];
+        for (u64 i = 1; ok && i <= n; i++) {
+            if (i < n && dst_off[i] == run_hi) { run_hi += dst_cap[i]; continue; }
+            if (run_hi > run_lo)
+                ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)c->st_dst.p + (run_lo - dst_lo), run_hi - run_lo,
+                                     cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            if (i < n) { run_lo = dst_off[i]; run_hi = dst_off[i] + dst_cap[i]; }
+        }
+        if (!ok || cudaStreamSynchronize(s) != cudaSuccess) rc = -(int)KZG_E_MEMORY;
+    }
+    free(h_tab);
+    return rc;
+}

@@ -1,0 +1,126 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the per-thread stage functions of the CUDA decoder
+// (kompressor_b200/csrc/kzg_stages.cuh -- the very code the kernels execute, compiled here as host
+// C++) in plain CPU loops, so scan / parse / link / Huffman / FSE / offsets logic and the packed
+// sequence-record format can be checked against libzstd without a GPU.  The execute step below is
+// a simple sequential stand-in for the CUDA execute kernel (which is warp-cooperative and only
+// testable on a GPU).  Never linked into libkzg.so.
+#include "../../kompressor_b200/csrc/kzg_stages.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+static u64 xxh64(const u8* p, u64 len) {
+    const u64 P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull,
+              P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    auto rotl = [](u64 x, int r) { return (x << r) | (x >> (64 - r)); };
+    auto round = [&](u64 a, u64 x) { return rotl(a + x * P2, 31) * P1; };
+    const u8* end = p + len;
+    u64 h;
+    if (len >= 32) {
+        u64 v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        while (end - p >= 32) { v1 = round(v1, kzg_rd64(p)); v2 = round(v2, kzg_rd64(p + 8)); v3 = round(v3, kzg_rd64(p + 16)); v4 = round(v4, kzg_rd64(p + 24)); p += 32; }
+        h = rotl(v1, 1) + rotl(v2, 7) + rotl(v3, 12) + rotl(v4, 18);
+        h = (h ^ round(0, v1)) * P1 + P4; h = (h ^ round(0, v2)) * P1 + P4; h = (h ^ round(0, v3)) * P1 + P4; h = (h ^ round(0, v4)) * P1 + P4;
+    } else h = P5;
+    h += len;
+    while (end - p >= 8) { h = rotl(h ^ round(0, kzg_rd64(p)), 27) * P1 + P4; p += 8; }
+    if (end - p >= 4) { h = rotl(h ^ ((u64)kzg_rd32(p) * P1), 23) * P2 + P3; p += 4; }
+    while (p < end) { h = rotl(h ^ ((u64)(*p) * P5), 11) * P1; p++; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* src_off, const u64* src_size, u64 n,
+                                    u8* dst, const u64* dst_off, const u64* dst_cap, u32* status, u64* out_size,
+                                    u64* seq_dump, u64 seq_dump_cap, u8* lit_dump, u64 lit_dump_cap) {
+    // padded, 16-byte aligned copy of the source (the device contract: aligned chunks around data are readable)
+    std::vector<u8> srcbuf(src_len + 64 + 16);
+    u8* src = srcbuf.data() + 16;
+    src = (u8*)(((uintptr_t)src + 15) & ~(uintptr_t)15);
+    memcpy(src, src_in, src_len);
+    u64 total_dst = 0;
+    for (u64 i = 0; i < n; i++) total_dst += dst_cap[i];
+    const u64 block_cap = n + src_len / 3 + 16;
+    std::vector<KzgFrame> frames(n);
+    std::vector<KzgBlock> blocks(block_cap);
+    std::vector<KzgCBlock> cblocks(block_cap);
+    std::vector<KzgFseDesc> fse(block_cap);
+    std::vector<KzgHufDesc> huf(block_cap);
+    std::vector<u32> hlist(block_cap), slist(block_cap);
+    std::vector<u8> lit(total_dst + 64 * block_cap + 4096 + 16);
+    std::vector<u64> seq(total_dst / 3 + 4096);
+    KzgCounters ctr;
+    memset(&ctr, 0, sizeof ctr);
+    KzgFseDesc def;
+    kzg_default_fse_desc(def);
+    u32 codes[96];
+    kzg_code_tables(codes, codes + 36);
+    KzgBatch B;
+    memset(&B, 0, sizeof B);
+    B.src = src; B.src_off = src_off; B.src_size = src_size; B.dst = dst; B.dst_off = dst_off; B.dst_cap = dst_cap;
+    B.status = status; B.out_size = out_size; B.n_frames = (u32)n; B.tile_bytes = KZG_BLOCK_MAX + 64;
+    B.frames = frames.data(); B.blocks = blocks.data(); B.cblocks = cblocks.data(); B.fse = fse.data(); B.huf = huf.data();
+    B.hlist = hlist.data(); B.slist = slist.data();
+    B.lit_pool = (u8*)(((uintptr_t)lit.data() + 15) & ~(uintptr_t)15); B.seq_pool = seq.data(); B.ctr = &ctr;
+    B.fse_default = &def; B.code_tables = codes; B.lit_cap = lit.size() - 32; B.seq_cap = seq.size();
+    B.block_cap = (u32)block_cap; B.cblock_cap = (u32)block_cap;
+    for (u32 i = 0; i < n; i++) kzg_stage_scan(B, i);
+    if (ctr.overflow) return -1;
+    for (u32 c = 0; c < ctr.n_cblocks; c++) kzg_stage_parse(B, c);
+    for (u32 i = 0; i < n; i++) kzg_stage_link(B, i);
+    // huffman: 4 "lanes" per block build the table, then each stream decodes
+    std::vector<u16> tab(1u << KZG_HUF_MAXBITS);
+    for (u32 h = 0; h < ctr.n_hblocks; h++) {
+        KzgCBlock* cb = &cblocks[hlist[h]];
+        if (cb->status_lit != KZG_OK || cb->huf_owner == KZG_INVALID_OWNER) continue;
+        const KzgHufDesc* hd = &huf[cb->huf_owner];
+        for (u32 st = 0; st < 4; st++) kzg_huf_build(tab.data(), hd->weight, hd->nsym, hd->maxbits, st, 4);
+        for (u32 st = 0; st < cb->n_streams; st++) kzg_stage_huf_stream(B, cb, st, tab.data(), hd->maxbits);
+    }
+    std::vector<u16> t3(1280);
+    for (u32 s = 0; s < ctr.n_sblocks; s++)
+        kzg_stage_fse_block(B, &cblocks[slist[s]], t3.data(), t3.data() + 512, t3.data() + 1024, codes, codes + 36);
+    for (u32 i = 0; i < n; i++) kzg_stage_offsets(B, i);
+    if (ctr.overflow) return -2;
+    // optional dumps (first compressed block order) for stage-by-stage comparison
+    if (seq_dump) { u64 m = ctr.seq_used < seq_dump_cap ? ctr.seq_used : seq_dump_cap; memcpy(seq_dump, seq.data(), m * 8); }
+    if (lit_dump) { u64 m = ctr.lit_used < lit_dump_cap ? ctr.lit_used : lit_dump_cap; memcpy(lit_dump, B.lit_pool, m); }
+    // sequential execute + finish
+    for (u32 f = 0; f < n; f++) {
+        KzgFrame& fr = frames[f];
+        u32 st = fr.status;
+        u8* fdst = dst + dst_off[f];
+        for (u32 k = 0; !st && k < fr.n_blocks; k++) {
+            const KzgBlock& blk = blocks[fr.first_block + k];
+            u8* out = fdst + blk.out_off;
+            if (blk.type == 0) memcpy(out, src + blk.src, blk.regen);
+            else if (blk.type == 1) memset(out, src[blk.src], blk.regen);
+            else {
+                const KzgCBlock& cb = cblocks[blk.cidx];
+                const u8* l = cb.lit_type >= 2 ? B.lit_pool + cb.lit_out : src + cb.src + cb.lit_src;
+                u32 lp = 0, op = 0;
+                for (u32 q = 0; q < cb.n_seq && !st; q++) {
+                    const u64 rec = B.seq_pool[cb.seq_out + q];
+                    const u32 lit_end = (u32)(rec >> 28) & 0x3FFFF, out_end = (u32)(rec >> 46);
+                    u32 off = kzg_rep_subst((u32)rec & KZG_OFF_MASK, cb.rep_init);
+                    const u32 ll = lit_end - lp;
+                    for (u32 j = 0; j < ll; j++) out[op + j] = cb.lit_type == 1 ? l[0] : l[lp + j];
+                    op += ll; lp = lit_end;
+                    const u32 ml = out_end - op;
+                    if (off == 0 || off >= KZG_OFF_INVALID || (u64)off > blk.out_off + op) { st = KZG_E_CORRUPTION; break; }
+                    for (u32 j = 0; j < ml; j++) out[op + j] = out[(i64)op + j - (i64)off];
+                    op += ml;
+                }
+                if (!st) for (u32 j = lp; j < cb.lit_regen; j++) out[op++] = cb.lit_type == 1 ? l[0] : l[j];
+                if (!st && op != blk.regen) st = KZG_E_GENERIC;
+            }
+        }
+        if (!st && fr.checksum_off != KZG_NONE) {
+            if ((u32)xxh64(fdst, fr.out_size) != kzg_rd32(src + src_off[f] + fr.checksum_off)) st = KZG_E_CHECKSUM_WRONG;
+        }
+        status[f] = st;
+        out_size[f] = st ? 0 : fr.out_size;
+    }
+    return 0;
+}
