@@ -5,6 +5,7 @@
 #include "kzg_entropy.cuh"
 
 #include <mutex>
+#include <vector>
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -43,6 +44,10 @@ struct kzg_ctx {
     u64 last_n_frames = 0;
     // staging for the host-pointer form
     DevBuf st_src, st_dst, st_tab;
+    // raw-content dictionary applied to every frame of subsequent batches
+    DevBuf dict;
+    u32 dict_size = 0;
+    std::vector<u8> dict_host;
 };
 
 static const char* err_name(u32 c) {
@@ -129,11 +134,29 @@ extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf* all[] = { &c->frames, &c->blocks, &c->cblocks, &c->fse, &c->huf, &c->hlist, &c->slist, &c->lit, &c->seq,
-                      &c->ctr, &c->consts, &c->st_src, &c->st_dst, &c->st_tab };
+                      &c->ctr, &c->consts, &c->st_src, &c->st_dst, &c->st_tab, &c->dict };
     for (DevBuf* b : all) b->release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+// Sets (dict != NULL) or clears the raw-content dictionary used as history prefix by the following
+// batches (reference: ZSTD_DCtx_loadDictionary at Wrapper.cpp:58-73). Formatted dictionaries
+// (magic 0xEC30A437: entropy tables + repeat offsets) are not supported yet -> parameter_unsupported.
+extern "C" int kzg_ctx_set_dictionary(kzg_ctx* c, const void* dict, size_t size) {
+    if (!c) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!dict || size == 0) { c->dict_size = 0; c->dict_host.clear(); return 0; }
+    if (size >= 8 && kzg_rd32((const u8*)dict) == KZG_DICT_MAGIC) return -40;
+    if (size > 0x7FFFFFFFu) return -(int)KZG_E_MEMORY;
+    if (c->dict_host.size() == size && memcmp(c->dict_host.data(), dict, size) == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    if (c->dict.ensure(size + 16)) return -(int)KZG_E_MEMORY;
+    CK(cudaMemcpy(c->dict.p, dict, size, cudaMemcpyHostToDevice));
+    c->dict_host.assign((const u8*)dict, (const u8*)dict + size);
+    c->dict_size = (u32)size;
+    return 0;
 }
 
 extern "C" void* kzg_host_alloc(size_t bytes) {
@@ -248,7 +271,7 @@ extern "C" int kzg_decompress_batch_device(kzg_ctx* c, const void* d_src, const 
     b.code_tables = (const u32*)((const u8*)c->consts.p + sizeof(KzgFseDesc));
     b.lit_cap = c->lit_cap; b.seq_cap = c->seq_cap;
     b.block_cap = (u32)c->block_cap; b.cblock_cap = (u32)c->cblock_cap;
-    b.dict = nullptr; b.dict_size = 0; b.dict_id = 0;
+    b.dict = (const u8*)c->dict.p; b.dict_size = c->dict_size; b.dict_id = 0;
     CK(cudaMemsetAsync(c->ctr.p, 0, sizeof(KzgCounters), stream));
     const int launches = kzg_launch_batch(b, c->sm_count, stream);
     CK(cudaGetLastError());

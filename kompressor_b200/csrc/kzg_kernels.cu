@@ -149,8 +149,16 @@ __device__ __forceinline__ void kzg_set_global(u8* dst, u32 byte, u32 n, u32 tid
 
 // One lane copies one match of <= KZG_LONG_ML bytes inside the tile. spos may be negative: that part
 // of the source lies in earlier blocks of the frame (already in global memory at gout[spos]).
-__device__ __forceinline__ void kzg_copy_match_lane(u8* tile, const u8* gout, u32 mdst, i32 spos, u32 ml, u32 off) {
-    while (spos < 0 && ml) { tile[mdst] = gout[spos]; mdst++; spos++; ml--; }
+// Byte at block-relative position p < 0: earlier output of the frame, or (before the frame start) the
+// raw-content dictionary that prefixes every frame of the batch.
+__device__ __forceinline__ u8 kzg_hist_byte(const u8* gout, i32 p, i64 boff, const u8* dict_end) {
+    const i64 fi = boff + p;
+    return fi >= 0 ? gout[p] : dict_end[fi];
+}
+
+__device__ __forceinline__ void kzg_copy_match_lane(u8* tile, const u8* gout, u32 mdst, i32 spos, u32 ml, u32 off,
+                                                    i64 boff, const u8* dict_end) {
+    while (spos < 0 && ml) { tile[mdst] = kzg_hist_byte(gout, spos, boff, dict_end); mdst++; spos++; ml--; }
     if (!ml) return;
     u8* q = tile + mdst;
     const u8* s = tile + spos;
@@ -192,6 +200,8 @@ __device__ bool kzg_exec_cblock(const KzgBatch& B, const KzgBlock& blk, u8* out,
     const u64* seqs = B.seq_pool + cb->seq_out;
     const u32 nb = (nseq + 31) >> 5;
     const u32 ri0 = cb->rep_init[0], ri1 = cb->rep_init[1], ri2 = cb->rep_init[2];
+    const i64 boff = (i64)blk.out_off;
+    const u8* dict_end = B.dict + B.dict_size;
     if (tid == 0) { sh.done = 0; sh.P = 0; sh.err = 0; }
 
     // ---- phase A: all literal runs (no dependencies)
@@ -261,7 +271,7 @@ __device__ bool kzg_exec_cblock(const KzgBatch& B, const KzgBlock& blk, u8* out,
             const bool ready = active && need <= hw;
             const u32 rm = __ballot_sync(0xFFFFFFFFu, ready);
             if (!rm) { __nanosleep(64); continue; }
-            if (ready && ml <= KZG_LONG_ML) kzg_copy_match_lane(tile, out, mdst, spos, ml, off);
+            if (ready && ml <= KZG_LONG_ML) kzg_copy_match_lane(tile, out, mdst, spos, ml, off, boff, dict_end);
             u32 lm = __ballot_sync(0xFFFFFFFFu, ready && ml > KZG_LONG_ML);
             while (lm) {
                 const u32 sl = __ffs(lm) - 1;
@@ -270,9 +280,9 @@ __device__ bool kzg_exec_cblock(const KzgBatch& B, const KzgBlock& blk, u8* out,
                           of = __shfl_sync(0xFFFFFFFFu, off, sl);
                 const i32 sp = __shfl_sync(0xFFFFFFFFu, spos, sl);
                 if (of >= nn) {
-                    for (u32 k = lane; k < nn; k += 32) { const i32 p = sp + (i32)k; tile[md + k] = p < 0 ? out[p] : tile[p]; }
+                    for (u32 k = lane; k < nn; k += 32) { const i32 p = sp + (i32)k; tile[md + k] = p < 0 ? kzg_hist_byte(out, p, boff, dict_end) : tile[p]; }
                 } else {   // overlapping: every byte equals one of the `of` bytes just before the match
-                    for (u32 k = lane; k < nn; k += 32) { const i32 p = sp + (i32)(k % of); tile[md + k] = p < 0 ? out[p] : tile[p]; }
+                    for (u32 k = lane; k < nn; k += 32) { const i32 p = sp + (i32)(k % of); tile[md + k] = p < 0 ? kzg_hist_byte(out, p, boff, dict_end) : tile[p]; }
                 }
             }
             if (ready) active = false;

@@ -1,0 +1,84 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol include/kzg.h
+declares; host-only entry points behave (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kzg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kzg_[A-Za-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(kzg_lib):
+    from kompressor_b200._lib import EXPORTS
+    syms = declared_symbols()
+    assert len(syms) >= 16
+    assert sorted(EXPORTS) == syms
+    for s in syms:
+        assert hasattr(kzg_lib, s), s
+
+
+def test_library_is_built_for_sm_100a():
+    import subprocess
+    from kompressor_b200._lib import LIB_PATH
+    out = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_error_names_and_codes(kzg_lib, libzstd):
+    for code in (1, 10, 12, 14, 16, 20, 22, 24, 30, 32, 40, 42, 44, 46, 62, 64, 66, 70, 72, 74, 80, 82):
+        assert kzg_lib.kzg_getErrorName((1 << 64) - code).decode() == libzstd.error_name(-code), code
+    assert kzg_lib.kzg_isError((1 << 64) - 20) == 1 and kzg_lib.kzg_isError(12345) == 0
+    assert kzg_lib.kzg_isError((1 << 64) - 120) == 0      # libzstd: error iff > (size_t)-120
+
+
+def test_scan_frames_matches_oracle(kzg_lib, oracle_mod, manifest):
+    from helpers import gbytes
+    from kompressor_b200.batch import scan_frames
+    names = [v["name"] for v in manifest["vectors"] if v["name"] not in ("skippable_then_hello", "two_frames")]
+    blob = b"".join(gbytes(n + ".zst") for n in names)
+    off, size, content, consumed = scan_frames(blob)
+    assert consumed == len(blob) and len(off) == len(names)
+    pos = 0
+    for i, n in enumerate(names):
+        assert int(off[i]) == pos and int(size[i]) == oracle_mod.find_frame_size(blob[pos:]) == len(gbytes(n + ".zst"))
+        pos += int(size[i])
+    sizes = {v["name"]: v["size"] for v in manifest["vectors"]}
+    for i, n in enumerate(names):
+        assert int(content[i]) >= sizes[n]
+    # truncated tail: stops at the last complete frame, no error
+    off2, _, _, consumed2 = scan_frames(blob[:-3])
+    assert len(off2) == len(names) - 1 and consumed2 == int(off[-1])
+    # unknown magic -> error -10
+    from kompressor_b200 import KzgError
+    with pytest.raises(KzgError):
+        scan_frames(b"garbage!garbage!")
+
+
+def test_no_cpu_fallback_without_gpu(kzg_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    assert kzg_lib.kzg_ctx_create(ctypes.byref(h), -1) == 64 and not h
+    assert not kzg_lib.kzg_createDCtx()
+    from kompressor_b200.zstd import IllegalStateException, ZstdDecompressor
+    with pytest.raises(IllegalStateException):
+        ZstdDecompressor()
+
+
+def test_product_never_touches_oracle():
+    pkg = os.path.join(ROOT, "kompressor_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text, f
+                assert "hostsim" not in text or f.endswith(".cuh"), f
