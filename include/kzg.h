@@ -97,6 +97,16 @@ typedef struct {
 } kzg_batch_stats;
 int kzg_last_batch_stats(kzg_ctx* ctx, kzg_batch_stats* out);
 
+/* Raw-content dictionary used as history prefix by the following batches (NULL clears it).
+ * Replaces ZSTD_DCtx_loadDictionary (Wrapper.cpp:58-73) on the batch layer. */
+int kzg_ctx_set_dictionary(kzg_ctx* ctx, const void* dict, size_t size);
+
+/* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline).
+ * kzg_last_stage_ms fills ms[i] / names[i] for the stages of the last finished batch and returns
+ * how many stages it wrote (0 if profiling was off). */
+int kzg_ctx_set_profiling(kzg_ctx* ctx, int enable);
+int kzg_last_stage_ms(kzg_ctx* ctx, float* ms, const char** names, int max_stages);
+
 /* ------------------------------------------------------------------ Layer B: streaming shim */
 typedef struct kzg_DCtx kzg_DCtx;
 typedef struct { const void* src; size_t size; size_t pos; } kzg_inBuffer;   /* == ZSTD_inBuffer */

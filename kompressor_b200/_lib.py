@@ -35,7 +35,7 @@ class OutBuffer(Structure):
 EXPORTS = [
     "kzg_isError", "kzg_getErrorName", "kzg_versionString", "kzg_ctx_create", "kzg_ctx_destroy", "kzg_scan_frames",
     "kzg_decompress_batch_device", "kzg_batch_finish", "kzg_decompress_batch_host", "kzg_host_alloc", "kzg_host_free",
-    "kzg_last_batch_stats", "kzg_createDCtx", "kzg_freeDCtx", "kzg_DCtx_loadDictionary", "kzg_decompressStream",
+    "kzg_last_batch_stats", "kzg_ctx_set_dictionary", "kzg_ctx_set_profiling", "kzg_last_stage_ms", "kzg_createDCtx", "kzg_freeDCtx", "kzg_DCtx_loadDictionary", "kzg_decompressStream",
 ]
 
 _lib = None
@@ -74,6 +74,12 @@ def lib() -> ctypes.CDLL:
     L.kzg_host_free.restype = None
     L.kzg_last_batch_stats.argtypes = [c_void_p, POINTER(BatchStats)]
     L.kzg_last_batch_stats.restype = c_int
+    L.kzg_ctx_set_dictionary.argtypes = [c_void_p, c_void_p, c_size_t]
+    L.kzg_ctx_set_dictionary.restype = c_int
+    L.kzg_ctx_set_profiling.argtypes = [c_void_p, c_int]
+    L.kzg_ctx_set_profiling.restype = c_int
+    L.kzg_last_stage_ms.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
+    L.kzg_last_stage_ms.restype = c_int
     if hasattr(L, "kzg_createDCtx"):
         L.kzg_createDCtx.restype = c_void_p
         L.kzg_freeDCtx.argtypes = [c_void_p]

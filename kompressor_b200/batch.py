@@ -142,6 +142,21 @@ class BatchDecoder:
                 return launches
         raise KzgError("workspace did not converge")
 
+    def set_profiling(self, enable: bool = True) -> None:
+        self._L.kzg_ctx_set_profiling(self._h, int(enable))
+
+    def stage_ms(self) -> dict:
+        """Per-stage device time (ms) of the last finished batch; {} if profiling is off."""
+        ms = (ctypes.c_float * 16)()
+        names = (ctypes.c_char_p * 16)()
+        n = self._L.kzg_last_stage_ms(self._h, ms, names, 16)
+        return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
+
+    def set_dictionary(self, dictionary: bytes | None) -> None:
+        rc = self._L.kzg_ctx_set_dictionary(self._h, dictionary, len(dictionary) if dictionary else 0)
+        if rc < 0:
+            raise KzgError(f"kzg_ctx_set_dictionary failed: {rc}")
+
     def stats(self) -> BatchStats:
         st = BatchStats()
         self._L.kzg_last_batch_stats(self._h, ctypes.byref(st))

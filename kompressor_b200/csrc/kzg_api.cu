@@ -48,6 +48,10 @@ struct kzg_ctx {
     DevBuf dict;
     u32 dict_size = 0;
     std::vector<u8> dict_host;
+    // optional per-stage CUDA events (kzg_ctx_set_profiling)
+    bool profiling = false;
+    cudaEvent_t ev[KZG_N_STAGES + 1] = {};
+    bool ev_valid = false;
 };
 
 static const char* err_name(u32 c) {
@@ -138,6 +142,7 @@ extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     for (DevBuf* b : all) b->release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (int i = 0; i <= KZG_N_STAGES; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
 
@@ -273,7 +278,8 @@ extern "C" int kzg_decompress_batch_device(kzg_ctx* c, const void* d_src, const 
     b.block_cap = (u32)c->block_cap; b.cblock_cap = (u32)c->cblock_cap;
     b.dict = (const u8*)c->dict.p; b.dict_size = c->dict_size; b.dict_id = 0;
     CK(cudaMemsetAsync(c->ctr.p, 0, sizeof(KzgCounters), stream));
-    const int launches = kzg_launch_batch(b, c->sm_count, stream);
+    const int launches = kzg_launch_batch(b, c->sm_count, stream, c->profiling ? c->ev : nullptr);
+    c->ev_valid = c->profiling;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(KzgCounters), cudaMemcpyDeviceToHost, stream));
     c->last_launches = (u32)launches;
@@ -296,6 +302,29 @@ extern "C" int kzg_batch_finish(kzg_ctx* c) {
     if (k.overflow & 8u) c->seq_cap = k.seq_used + (k.seq_used >> 4) + 4096;
     if (k.overflow & 16u) c->tile_bytes = KZG_BLOCK_MAX + 64;
     return 1;
+}
+
+extern "C" int kzg_ctx_set_profiling(kzg_ctx* c, int enable) {
+    if (!c) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(cudaSetDevice(c->device));
+    if (enable && !c->ev[0])
+        for (int i = 0; i <= KZG_N_STAGES; i++) CK(cudaEventCreate(&c->ev[i]));
+    c->profiling = enable != 0;
+    c->ev_valid = false;
+    return 0;
+}
+
+extern "C" int kzg_last_stage_ms(kzg_ctx* c, float* ms, const char** names, int max_stages) {
+    if (!c || !ms) return -(int)KZG_E_GENERIC;
+    if (!c->ev_valid) return 0;
+    CK(cudaSetDevice(c->device));
+    int n = max_stages < KZG_N_STAGES ? max_stages : KZG_N_STAGES;
+    for (int i = 0; i < n; i++) {
+        CK(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+        if (names) names[i] = kzg_stage_names[i];
+    }
+    return n;
 }
 
 extern "C" int kzg_last_batch_stats(kzg_ctx* c, kzg_batch_stats* out) {

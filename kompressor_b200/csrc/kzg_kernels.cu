@@ -416,7 +416,9 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
 // ------------------------------------------------------------------------------------------------
 static bool g_attr_done = false;
 
-int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream) {
+const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "huffman", "fse", "offsets", "execute", "finish" };
+
+int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
     const size_t huf_smem = (size_t)KZG_HUF_WARPS * 8 * KZG_HUF_TABLE_BYTES;
     const size_t fse_smem = 96 * 4 + (size_t)KZG_FSE_WARPS * KZG_FSE_LANES * KZG_FSE_CELLS * 2;
     const size_t exec_smem = b.tile_bytes;
@@ -428,16 +430,28 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream) {
     }
     const u32 n = b.n_frames;
     if (n == 0) return 0;
+    int k = 0;
+#define KZG_MARK() do { if (ev) cudaEventRecord(ev[k], stream); k++; } while (0)
     const u32 fgrid = (n + 127) / 128;
+    KZG_MARK();
     kzg_scan_kernel<<<fgrid, 128, 0, stream>>>(b);
+    KZG_MARK();
     const u32 pgrid = (u32)min((u64)(b.cblock_cap + 63) / 64, (u64)sm_count * 16);
     kzg_parse_kernel<<<pgrid ? pgrid : 1, 64, 0, stream>>>(b);
+    KZG_MARK();
     kzg_link_kernel<<<fgrid, 128, 0, stream>>>(b);
+    KZG_MARK();
     kzg_huf_kernel<<<sm_count * 3, KZG_HUF_WARPS * 32, huf_smem, stream>>>(b);
+    KZG_MARK();
     kzg_fse_kernel<<<sm_count, KZG_FSE_WARPS * 32, fse_smem, stream>>>(b);
+    KZG_MARK();
     kzg_offsets_kernel<<<fgrid, 128, 0, stream>>>(b);
+    KZG_MARK();
     const int exec_per_sm = (int)((227 * 1024) / (exec_smem + 1024));
     kzg_exec_kernel<<<sm_count * (exec_per_sm < 1 ? 1 : exec_per_sm), KZG_EXEC_THREADS, exec_smem, stream>>>(b);
+    KZG_MARK();
     kzg_finish_kernel<<<(n * 4 + 127) / 128, 128, 0, stream>>>(b);
-    return 8;
+    KZG_MARK();
+#undef KZG_MARK
+    return KZG_N_STAGES;
 }

@@ -17,7 +17,7 @@
 #include <string.h>
 #include <vector>
 
-extern "C" int kzg_ctx_set_dictionary(kzg_ctx* ctx, const void* dict, size_t size);
+
 
 namespace {
 std::mutex g_mu;                 // one shared device context per process; batches are serialised
