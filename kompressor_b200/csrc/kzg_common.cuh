@@ -122,13 +122,14 @@ struct KzgFseDesc {         // entropy description parsed from a compressed bloc
     u8 log[3];              // accuracy logs; for RLE mode log = 0 and norm[t][0] = symbol
     u8 nsym[3];
     u8 kind[3];             // 0 none, 1 RLE, 2 FSE
-    u8 pad[3];
+    u8 pad[7];              // sizeof == 400: every norm[t] row stays 16-byte aligned in an array
 };
 
 struct KzgHufDesc {
     u8 weight[256];
     u32 nsym;               // number of weights including the implicit last one
     u32 maxbits;
+    u32 pad[2];             // sizeof == 272 (16-byte multiple)
 };
 
 struct KzgCounters {
@@ -196,3 +197,6 @@ KZG_HD u32 kzg_funnel_r(u32 lo, u32 hi, u32 sh) {   // low 32 bits of (hi:lo) >>
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 #endif
 }
+
+static_assert(sizeof(KzgFseDesc) == 400, "KzgFseDesc rows must stay 16-byte aligned");
+static_assert(sizeof(KzgHufDesc) == 272, "KzgHufDesc must be a 16-byte multiple");

@@ -10,33 +10,47 @@
 //   nbBits = log - floor(log2(next)),  baseline = (next << nbBits) - (1 << log).
 // 2-byte cells halve the shared-memory footprint (2560 B per block for logs 9/8/9), which is what
 // bounds how many blocks one SM decodes concurrently.
-KZG_HD void kzg_fse_build(u16* tab, const i16* norm, u32 nsym, u32 log) {
+// 16-byte copy (global -> shared on the device); both pointers 16-byte aligned.
+KZG_HD void kzg_copy16(void* dst, const void* src) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+#else
+    memcpy(dst, src, 16);
+#endif
+}
+
+// `scratch` (16-byte aligned, >= 2*ceil8(nsym) bytes, thread-private shared memory) first receives the
+// normalised counts with wide loads, then serves as the per-symbol `next` counters: no per-element
+// global or local-memory round trip sits on the build's dependency chain.
+// scratch encoding: count, or 0x8001 for a "less than one" (-1) symbol.
+KZG_HD void kzg_fse_build(u16* tab, const i16* norm, u32 nsym, u32 log, u16* scratch) {
     const u32 size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
     u32 high = size, pos = 0;
-    u16 next[64];
+    const u32 nchunks = (nsym + 7) >> 3;
+    for (u32 k = 0; k < nchunks; k++) kzg_copy16(scratch + 8 * k, norm + 8 * k);
     for (u32 s = 0; s < nsym; s++) {
-        const i32 c = norm[s];
-        if (c == -1) { tab[--high] = (u16)s; next[s] = 1; }
-        else next[s] = (u16)c;
+        if (scratch[s] == 0xFFFFu) { tab[--high] = (u16)s; scratch[s] = 0x8001u; }
     }
     for (u32 s = 0; s < nsym; s++) {
-        const i32 c = norm[s];
-        for (i32 i = 0; i < c; i++) {
+        const u32 v = scratch[s];
+        const u32 c = (v & 0x8000u) ? 0u : v;
+        for (u32 i = 0; i < c; i++) {
             tab[pos] = (u16)s;
             do { pos = (pos + step) & mask; } while (pos >= high);
         }
     }
     for (u32 i = 0; i < size; i++) {
         const u32 s = tab[i];
-        const u32 n = next[s]++;
-        tab[i] = (u16)((n << 6) | s);
+        const u32 v = scratch[s];
+        scratch[s] = (u16)(v + 1);
+        tab[i] = (u16)(((v & 0x7FFFu) << 6) | s);
     }
 }
 
 // Builds table `t` (0 LL, 1 OF, 2 ML) described by `d` into tab; returns its accuracy log.
-KZG_HD u32 kzg_fse_build_desc(u16* tab, const KzgFseDesc* d, u32 t) {
+KZG_HD u32 kzg_fse_build_desc(u16* tab, const KzgFseDesc* d, u32 t, u16* scratch) {
     if (d->kind[t] == 1) { tab[0] = (u16)((1u << 6) | (u32)d->norm[t][0]); return 0; }
-    kzg_fse_build(tab, d->norm[t], d->nsym[t], d->log[t]);
+    kzg_fse_build(tab, d->norm[t], d->nsym[t], d->log[t], scratch);
     return d->log[t];
 }
 
@@ -49,7 +63,7 @@ inline void kzg_default_fse_desc(KzgFseDesc& d) {
     d.log[0] = 6; d.log[1] = 5; d.log[2] = 6;
     d.nsym[0] = 36; d.nsym[1] = 29; d.nsym[2] = 53;
     d.kind[0] = d.kind[1] = d.kind[2] = 2;
-    d.pad[0] = d.pad[1] = d.pad[2] = 0;
+    for (int i = 0; i < 7; i++) d.pad[i] = 0;
 }
 
 // Literal-length / match-length code tables packed as (extra_bits << 24) | baseline (Appendix A.6).
@@ -64,21 +78,36 @@ inline void kzg_code_tables(u32* ll36, u32* ml53) {
 
 // ---------------------------------------------------------------------------------------------
 // Huffman decode table (Appendix A.4), 2 bytes per entry: symbol | code_length << 8.
-// `lane` of `nlanes` threads cooperate on one table: every lane walks the (cheap) position loop and
-// fills the spans of every nlanes-th coded symbol.  Spans are powers of two and naturally aligned.
-KZG_HD void kzg_huf_build(u16* tab, const u8* weights, u32 nsym, u32 maxbits, u32 lane, u32 nlanes) {
-    u32 start[KZG_HUF_MAXBITS + 2];
-    for (u32 w = 0; w <= KZG_HUF_MAXBITS + 1; w++) start[w] = 0;
-    for (u32 s = 0; s < nsym; s++) start[weights[s]]++;
+// The four threads that will decode a block's four streams build its table together. Each lane owns
+// the 64 symbols [64*lane, 64*lane+64): it stages their weights with wide loads (phase 1), counts them,
+// derives where its symbols start inside every weight class (phase 2) and fills their spans (phase 3).
+// Spans are powers of two and naturally aligned. The caller synchronises the lanes between phases.
+struct KzgHufScratch { u8 w[256]; u16 cnt[4][16]; u16 st[4][16]; };   // 512 B per table, shared memory
+
+KZG_HD void kzg_huf_build_phase1(KzgHufScratch* sc, const u8* weights, u32 nsym, u32 lane) {
+    for (u32 k = 0; k < 4; k++) kzg_copy16(sc->w + 64 * lane + 16 * k, weights + 64 * lane + 16 * k);
+    for (u32 w = 0; w < 16; w++) sc->cnt[lane][w] = 0;
+    const u32 lo = 64 * lane, hi = nsym < lo + 64 ? nsym : lo + 64;
+    for (u32 s = lo; s < hi; s++) sc->cnt[lane][sc->w[s] & 15]++;
+}
+
+KZG_HD void kzg_huf_build_phase2(KzgHufScratch* sc, u32 maxbits, u32 lane) {
     u32 pos = 0;
-    for (u32 w = 1; w <= maxbits; w++) { const u32 c = start[w]; start[w] = pos; pos += c << (w - 1); }
-    u32 ord = 0;
-    for (u32 s = 0; s < nsym; s++) {
-        const u32 w = weights[s];
+    for (u32 w = 1; w <= maxbits; w++) {
+        u32 before = 0, tot = 0;
+        for (u32 l = 0; l < 4; l++) { const u32 c = sc->cnt[l][w]; if (l < lane) before += c; tot += c; }
+        sc->st[lane][w] = (u16)(pos + (before << (w - 1)));
+        pos += tot << (w - 1);
+    }
+}
+
+KZG_HD void kzg_huf_build_phase3(u16* tab, KzgHufScratch* sc, u32 nsym, u32 maxbits, u32 lane) {
+    const u32 lo = 64 * lane, hi = nsym < lo + 64 ? nsym : lo + 64;
+    for (u32 s = lo; s < hi; s++) {
+        const u32 w = sc->w[s];
         if (w == 0 || w > maxbits) continue;
-        const u32 span = 1u << (w - 1), p = start[w];
-        start[w] = p + span;
-        if ((ord++ % nlanes) != lane) continue;
+        const u32 span = 1u << (w - 1), p = sc->st[lane][w];
+        sc->st[lane][w] = (u16)(p + span);
         const u32 e = s | ((maxbits + 1 - w) << 8);
         if (span == 1) { tab[p] = (u16)e; continue; }
         const u32 e2 = e | (e << 16);
@@ -89,7 +118,7 @@ KZG_HD void kzg_huf_build(u16* tab, const u8* weights, u32 nsym, u32 maxbits, u3
 
 // One Huffman stream: decodes exactly n symbols from [src, src+size) into dst. Returns 0 or an error.
 KZG_HD u32 kzg_huf_decode_stream(const u8* src, u32 size, const u16* tab, u32 maxbits, u8* dst, u32 n) {
-    KzgBwd b;
+    KzgBwdQ b;
     if (!b.init(src, size)) return KZG_E_CORRUPTION;
     const u32 shift = 64 - maxbits;
     u32 i = 0;
@@ -107,6 +136,7 @@ KZG_HD u32 kzg_huf_decode_stream(const u8* src, u32 size, const u16* tab, u32 ma
     }
     // body: 16 symbols per 16-byte store
     while (i + 16 <= n) {
+        b.advance();                              // warp-uniform point (every 16 symbols)
         u32 v[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -122,6 +152,7 @@ KZG_HD u32 kzg_huf_decode_stream(const u8* src, u32 size, const u16* tab, u32 ma
 #endif
         i += 16;
     }
+    b.advance();
     while (i < n) {
         b.ensure32();
         u32 s; KZG_HUF_SYM(s);
@@ -148,7 +179,7 @@ KZG_HD void kzg_decode_sequences(const u8* bits, u32 size, u32 nseq,
                                  const u16* tLL, u32 logLL, const u16* tOF, u32 logOF, const u16* tML, u32 logML,
                                  const u32* llx, const u32* mlx, u32 rep0, u32 rep1, u32 rep2,
                                  u32 lit_regen, u32 block_max, u64* out, KzgSeqOut& res) {
-    KzgBwd b;
+    KzgBwdQ b;
     res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;
     res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
     if (!b.init(bits, size)) return;
@@ -158,6 +189,7 @@ KZG_HD void kzg_decode_sequences(const u8* bits, u32 size, u32 nseq,
     u32 lit_end = 0, out_end = 0;
     const u32 szLL = 1u << logLL, szOF = 1u << logOF, szML = 1u << logML;
     for (u32 i = 0; i < nseq; i++) {
+        if ((i & 7u) == 7u) b.advance();          // warp-uniform point: the only place global loads are issued
         const u32 eLL = tLL[sLL], eOF = tOF[sOF], eML = tML[sML];
         const u32 ofc = eOF & 63u;
         const u32 pLL = llx[eLL & 63u], pML = mlx[eML & 63u];

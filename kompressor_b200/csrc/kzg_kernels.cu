@@ -37,14 +37,16 @@ __global__ void __launch_bounds__(128) kzg_link_kernel(KzgBatch B) {
 
 // ------------------------------------------------------------------------------------------------
 // huffman: one warp decodes 8 blocks at a time = 32 streams, one thread per stream. The four threads
-// of a block build its 2^maxbits-entry table together in shared memory (4 KiB per block).
+// of a block build its 2^maxbits-entry table together in shared memory (4 KiB + 512 B scratch per block).
 #define KZG_HUF_WARPS 2
 #define KZG_HUF_TABLE_BYTES ((1u << KZG_HUF_MAXBITS) * 2u)
+#define KZG_HUF_SMEM (KZG_HUF_WARPS * 8 * (KZG_HUF_TABLE_BYTES + sizeof(KzgHufScratch)))
 __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B) {
     extern __shared__ uint4 smem4[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 hb = lane >> 2, st = lane & 3;
     u16* tab = reinterpret_cast<u16*>(smem4) + (size_t)(warp * 8 + hb) * (KZG_HUF_TABLE_BYTES / 2);
+    KzgHufScratch* sc = reinterpret_cast<KzgHufScratch*>(reinterpret_cast<u8*>(smem4) + KZG_HUF_WARPS * 8 * KZG_HUF_TABLE_BYTES) + (warp * 8 + hb);
     if (B.ctr->overflow & 3u) return;
     const u32 n = B.ctr->n_hblocks;
     for (;;) {
@@ -59,12 +61,16 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
             cb = &B.cblocks[B.hlist[h]];
             valid = cb->status_lit == KZG_OK && cb->huf_owner != KZG_INVALID_OWNER;
         }
-        u32 maxbits = 0;
+        u32 maxbits = 0, nsym = 0;
         if (valid) {
             const KzgHufDesc* hd = &B.huf[cb->huf_owner];
-            maxbits = hd->maxbits;
-            kzg_huf_build(tab, hd->weight, hd->nsym, maxbits, st, 4);
+            maxbits = hd->maxbits; nsym = hd->nsym;
+            kzg_huf_build_phase1(sc, hd->weight, nsym, st);
         }
+        __syncwarp();
+        if (valid) kzg_huf_build_phase2(sc, maxbits, st);
+        __syncwarp();
+        if (valid) kzg_huf_build_phase3(tab, sc, nsym, maxbits, st);
         __syncwarp();
         if (valid && st < cb->n_streams) kzg_stage_huf_stream(B, cb, st, tab, maxbits);
         __syncwarp();
@@ -73,21 +79,26 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
 
 // ------------------------------------------------------------------------------------------------
 // fse: one thread per block runs the sequential sequence state machine; each thread owns 2560 B of
-// shared memory for its three decode tables (LL 512, ML 512, OF 256 cells of 2 bytes).
+// shared memory for its three decode tables (LL 512, ML 512, OF 256 cells of 2 bytes) + 80 B scratch.
 #define KZG_FSE_WARPS 3
-#define KZG_FSE_LANES 30            // blocks per warp (30 * 3 * 2560 B = 230400 B of the 227 KiB)
+#define KZG_FSE_LANES 29            // blocks per warp: 87 * (2560 + 80) + 384 = 230064 B of the 227 KiB
 #define KZG_FSE_CELLS 1280
+#define KZG_FSE_SCR 40              // u16 per lane
+#define KZG_FSE_SMEM (96 * 4 + KZG_FSE_WARPS * KZG_FSE_LANES * (KZG_FSE_CELLS + KZG_FSE_SCR) * 2)
 __global__ void __launch_bounds__(KZG_FSE_WARPS * 32) kzg_fse_kernel(KzgBatch B) {
     extern __shared__ uint4 smem4[];
     u32* llx = reinterpret_cast<u32*>(smem4);      // 36 + 53 packed code entries (+ pad to 96)
     u32* mlx = llx + 36;
-    u16* tabs = reinterpret_cast<u16*>(llx + 96);
+    u16* scr = reinterpret_cast<u16*>(llx + 96);
+    u16* tabs = scr + KZG_FSE_WARPS * KZG_FSE_LANES * KZG_FSE_SCR;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 89) llx[threadIdx.x] = B.code_tables[threadIdx.x];
     __syncthreads();
-    u16* tLL = tabs + (size_t)(warp * KZG_FSE_LANES + (lane < KZG_FSE_LANES ? lane : 0)) * KZG_FSE_CELLS;
+    const u32 slot = warp * KZG_FSE_LANES + (lane < KZG_FSE_LANES ? lane : 0);
+    u16* tLL = tabs + (size_t)slot * KZG_FSE_CELLS;
     u16* tML = tLL + 512;
     u16* tOF = tLL + 1024;
+    u16* scrLL = scr + (size_t)slot * KZG_FSE_SCR;
     if (B.ctr->overflow & 3u) return;
     const u32 n = B.ctr->n_sblocks;
     for (;;) {
@@ -96,7 +107,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32) kzg_fse_kernel(KzgBatch B)
         g = __shfl_sync(0xFFFFFFFFu, g, 0);
         if (g * KZG_FSE_LANES >= n) break;
         const u32 s = g * KZG_FSE_LANES + lane;
-        if (lane < KZG_FSE_LANES && s < n) kzg_stage_fse_block(B, &B.cblocks[B.slist[s]], tLL, tML, tOF, llx, mlx);
+        if (lane < KZG_FSE_LANES && s < n) kzg_stage_fse_block(B, &B.cblocks[B.slist[s]], tLL, tML, tOF, scrLL, llx, mlx);
         __syncwarp();
     }
 }
@@ -419,8 +430,8 @@ static bool g_attr_done = false;
 const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "huffman", "fse", "offsets", "execute", "finish" };
 
 int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
-    const size_t huf_smem = (size_t)KZG_HUF_WARPS * 8 * KZG_HUF_TABLE_BYTES;
-    const size_t fse_smem = 96 * 4 + (size_t)KZG_FSE_WARPS * KZG_FSE_LANES * KZG_FSE_CELLS * 2;
+    const size_t huf_smem = KZG_HUF_SMEM;
+    const size_t fse_smem = KZG_FSE_SMEM;
     const size_t exec_smem = b.tile_bytes;
     if (!g_attr_done) {
         cudaFuncSetAttribute(kzg_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem);

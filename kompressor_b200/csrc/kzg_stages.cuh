@@ -164,13 +164,15 @@ KZG_HD void kzg_stage_huf_stream(const KzgBatch& B, KzgCBlock* cb, u32 st, const
 }
 
 // fse: build the three tables of block cb into tLL/tML/tOF and run the sequence state machine
-KZG_HD void kzg_stage_fse_block(const KzgBatch& B, KzgCBlock* cb, u16* tLL, u16* tML, u16* tOF, const u32* llx,
-                                const u32* mlx) {
+// scrLL: >= 80 B of 16-byte aligned scratch for the LL build; the ML and OF builds borrow the
+// (not yet built) LL table area as scratch.
+KZG_HD void kzg_stage_fse_block(const KzgBatch& B, KzgCBlock* cb, u16* tLL, u16* tML, u16* tOF, u16* scrLL,
+                                const u32* llx, const u32* mlx) {
     if (cb->status_seq != KZG_OK || cb->status_lit != KZG_OK) return;
     const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-    const u32 logLL = kzg_fse_build_desc(tLL, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
-    const u32 logOF = kzg_fse_build_desc(tOF, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
-    const u32 logML = kzg_fse_build_desc(tML, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
+    const u32 logML = kzg_fse_build_desc(tML, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2, tLL);
+    const u32 logOF = kzg_fse_build_desc(tOF, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1, tLL);
+    const u32 logLL = kzg_fse_build_desc(tLL, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0, scrLL);
     u32 r0 = 1, r1 = 4, r2 = 8;
     if (!cb->first_in_frame) { r0 = KZG_OFF_SYM | 0; r1 = KZG_OFF_SYM | 1; r2 = KZG_OFF_SYM | 2; }
     KzgSeqOut res;

@@ -75,12 +75,16 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
         KzgCBlock* cb = &cblocks[hlist[h]];
         if (cb->status_lit != KZG_OK || cb->huf_owner == KZG_INVALID_OWNER) continue;
         const KzgHufDesc* hd = &huf[cb->huf_owner];
-        for (u32 st = 0; st < 4; st++) kzg_huf_build(tab.data(), hd->weight, hd->nsym, hd->maxbits, st, 4);
+        alignas(16) KzgHufScratch sc;
+        for (u32 st = 0; st < 4; st++) kzg_huf_build_phase1(&sc, hd->weight, hd->nsym, st);
+        for (u32 st = 0; st < 4; st++) kzg_huf_build_phase2(&sc, hd->maxbits, st);
+        for (u32 st = 0; st < 4; st++) kzg_huf_build_phase3(tab.data(), &sc, hd->nsym, hd->maxbits, st);
         for (u32 st = 0; st < cb->n_streams; st++) kzg_stage_huf_stream(B, cb, st, tab.data(), hd->maxbits);
     }
-    std::vector<u16> t3(1280);
+    alignas(16) static u16 t3[1280];
+    alignas(16) static u16 scrLL[40];
     for (u32 s = 0; s < ctr.n_sblocks; s++)
-        kzg_stage_fse_block(B, &cblocks[slist[s]], t3.data(), t3.data() + 512, t3.data() + 1024, codes, codes + 36);
+        kzg_stage_fse_block(B, &cblocks[slist[s]], t3, t3 + 512, t3 + 1024, scrLL, codes, codes + 36);
     for (u32 i = 0; i < n; i++) kzg_stage_offsets(B, i);
     if (ctr.overflow) return -2;
     // optional dumps (first compressed block order) for stage-by-stage comparison
