@@ -1,0 +1,298 @@
+// Sequence stage (s4) for sm_100a: FSE decode-table build + the ZSTD_decodeSequence state machine,
+// one GPU thread per compressed block, 32 blocks per warp.  Device-only code.
+//
+// The state machine is a serial dependency chain per block (state -> table cell -> bit count -> bits
+// -> next state), so the kernel is latency-bound and the design goal is the shortest chain with the
+// fewest instructions, with no divergence inside a warp:
+//   * tables live in shared memory, interleaved by lane: cell i of lane L is the u16 at byte
+//     (i << 6) + (L << 1) of the warp's table area, so a lookup costs one shift-add and lanes collide at
+//     most pairwise (two lanes share a 32-bit bank column);
+//   * the backward bitstream is staged by cp.async (LDGSTS, no destination register, so no per-warp
+//     scoreboard stall) into a per-lane ring of eight 16-byte chunks (128 contiguous bytes per lane);
+//     copies are issued only at warp-uniform points (every 4 sequences), sized so that the ring always
+//     covers the most bits four sequences can consume (4 x 89);
+//   * every sequence re-reads a 64-bit window at its current bit position from that ring (3 LDS + 2
+//     funnel shifts, off the critical chain) and extracts all six bit fields with clamped funnel
+//     shifts: no refill branches, no window register rotation;
+//   * repeat-offset history is kept in registers and updated with selects.
+// What libzstd does here is ZSTD_decodeSequence / ZSTD_buildFSETable, reached from the reference through
+// ZSTD_decompressStream (kompressor-zstd--nativelib/src/jvmCommonMain/jni/Wrapper.cpp:178).
+#pragma once
+#include "kzg_stages.cuh"
+
+#define KZG_FSE_WARPS 2
+#define KZG_FSE_CELLS 1280                                  // LL 512 | ML 512 | OF 256
+#define KZG_FSE_TAB_BYTES (KZG_FSE_CELLS * 64)              // per warp: 32 lanes x 1280 cells x 2 B
+#define KZG_FSE_RING_CHUNKS 8
+#define KZG_FSE_RING_BYTES (KZG_FSE_RING_CHUNKS * 512)      // per warp: 32 lanes x (8 chunks x 16 B, contiguous per lane)
+#define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
+#define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_WARPS * (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES))
+#define KZG_FSE_SERVICE 4                                   // sequences between ring service points
+
+namespace kzg_fse {
+
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 lds16(u32 a) { u16 v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((u16)v)); }
+__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Per-lane scratch during the table build = the lane's (still idle) bitstream ring: 64 u16.
+__device__ __forceinline__ u32 scr_addr(u32 ring, u32 j) { return ring + (j << 1); }
+
+// Builds one decode table in the lane's column. Cell = symbol | next << 6 (see kzg_entropy.cuh).
+// tab: shared address of the lane's cell 0 of this table; ring: shared address of the lane's ring.
+__device__ __forceinline__ u32 build_table(u32 tab, u32 ring, const KzgFseDesc* d, u32 t) {
+    if (d->kind[t] == 1) { sts16(tab, (1u << 6) | (u32)(u16)d->norm[t][0]); return 0; }
+    const u32 log = d->log[t], nsym = d->nsym[t];
+    const u32 size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    const i16* norm = d->norm[t];
+    u32 high = size;
+    for (u32 s = 0; s < nsym; s++) {
+        const i32 c = norm[s];
+        u32 v = (u32)c & 0x7FFFu;
+        if (c < 0) { high--; sts16(tab + (high << 6), s); v = 0x8001u; }
+        sts16(scr_addr(ring, s), v);
+    }
+    // spread: one flat loop over the (high) cells that are not "less than one" symbols
+    {
+        u32 pos = 0, s = 0, rem = 0;
+        for (u32 j = 0; j < high; j++) {
+            while (rem == 0 && s < 64u) {
+                const u32 v = lds16(scr_addr(ring, s));
+                rem = (v & 0x8000u) ? 0u : v;
+                s++;
+            }
+            sts16(tab + (pos << 6), s - 1);
+            rem--;
+            do { pos = (pos + step) & mask; } while (pos >= high);
+        }
+    }
+    for (u32 i = 0; i < size; i++) {
+        const u32 a = tab + (i << 6);
+        const u32 s = lds16(a);
+        const u32 sa = scr_addr(ring, s);
+        const u32 v = lds16(sa);
+        sts16(sa, v + 1);
+        sts16(a, ((v & 0x7FFFu) << 6) | s);
+    }
+    return log;
+}
+
+// Generic (slow, rare) backward bit read straight from global memory: n <= 32 bits below position P.
+__device__ __noinline__ u32 slow_bits(const u32* base32, i32 P, u32 n) {
+    if (n == 0) return 0;
+    const i32 k = P >> 5;
+    const u32 q = (u32)P & 31u;
+    const u32 w1 = k >= 0 ? base32[k] : 0u, w0 = k >= 1 ? base32[k - 1] : 0u;
+    return __funnelshift_r(w0, w1, q) >> (32 - n);
+}
+
+struct Result { u32 status, regen, lit_used, rep0, rep1, rep2; };
+
+}  // namespace kzg_fse
+
+__global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch B) {
+    using namespace kzg_fse;
+    extern __shared__ uint4 smem4[];
+    u32* llx = reinterpret_cast<u32*>(smem4);
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 k = threadIdx.x; k < KZG_FSE_CODE_WORDS; k += blockDim.x) llx[k] = k < 89 ? B.code_tables[k] : 0u;
+    __syncthreads();
+    const u32 s_llx = smem_addr(llx), s_mlx = s_llx + 36 * 4;
+    const u32 s_warp = s_llx + KZG_FSE_CODE_WORDS * 4 + warp * (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES);
+    const u32 s_tab = s_warp + (lane << 1);
+    const u32 s_ring = s_warp + KZG_FSE_TAB_BYTES + (lane << 7);
+    const u32 tLL = s_tab, tML = s_tab + (512u << 6), tOF = s_tab + (1024u << 6);
+    if (B.ctr->overflow & 3u) return;
+    const u32 n = B.ctr->n_sblocks;
+
+    for (;;) {
+        u32 g = 0;
+        if (lane == 0) g = atomicAdd(&B.ctr->ticket_fse, 1u);
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        if (g * 32 >= n) break;
+        const u32 si = g * 32 + lane;
+        KzgCBlock* cb = nullptr;
+        u32 nseq = 0;
+        if (si < n) {
+            cb = &B.cblocks[B.slist[si]];
+            if (cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) nseq = cb->n_seq;
+        }
+        // ---- tables (per lane, in its own column; the ring doubles as build scratch)
+        u32 logLL = 0, logOF = 0, logML = 0;
+        if (nseq) {
+            const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
+            logLL = build_table(tLL, s_ring, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
+            logOF = build_table(tOF, s_ring, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
+            logML = build_table(tML, s_ring, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
+        }
+        __syncwarp();
+        // ---- bitstream set-up
+        Result res;
+        res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;
+        u32 rep0 = 1, rep1 = 4, rep2 = 8;
+        if (nseq && !cb->first_in_frame) { rep0 = KZG_OFF_SYM | 0; rep1 = KZG_OFF_SYM | 1; rep2 = KZG_OFF_SYM | 2; }
+        res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
+        const u8* base = nullptr;
+        i32 P = 0, lowbits = 0, next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
+        u64* out = nullptr;
+        u32 lit_regen = 0, block_max = 0;
+        if (nseq) {
+            const u8* start = B.src + cb->src + cb->seq_src;
+            const u32 size = cb->seq_size;
+            const u32 last = size ? start[size - 1] : 0u;
+            if (last == 0) nseq = 0;                       // no padding marker: corrupt (status stays CORRUPTION)
+            else {
+                base = (const u8*)((uintptr_t)start & ~(uintptr_t)15);
+                lowbits = (i32)(8u * (u32)(start - base));
+                P = lowbits + (i32)(8u * (size - 1)) + kzg_highbit(last);
+                out = B.seq_pool + cb->seq_out;
+                lit_regen = cb->lit_regen;
+                block_max = B.frames[cb->frame].block_max;
+                next_c = P >> 7;
+                for (int r = 0; r < KZG_FSE_RING_CHUNKS; r++)
+                    if (next_c >= 0) { cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4)); next_c--; }
+            }
+        }
+        cp_commit();
+        cp_wait<0>();
+        ready_lo = pend1 = pend2 = next_c + 1;
+        const u32* base32 = reinterpret_cast<const u32*>(base);
+
+        // 64-bit window [P-64, P) -> hi:lo from the lane's ring (word w of the stream sits at (w & 31) * 4)
+#define KZG_FSE_WINDOW(hi, lo)                                                     \
+        {                                                                          \
+            const u32 t_ = (u32)(P >> 3), q_ = (u32)P & 31u;                       \
+            const u32 w2_ = lds32(s_ring + (t_ & 0x7Cu));                          \
+            const u32 w1_ = lds32(s_ring + ((t_ - 4u) & 0x7Cu));                   \
+            const u32 w0_ = lds32(s_ring + ((t_ - 8u) & 0x7Cu));                   \
+            hi = __funnelshift_r(w1_, w2_, q_);                                    \
+            lo = __funnelshift_r(w0_, w1_, q_);                                    \
+        }
+
+        // ---- initial states: LL, OF, ML (Appendix A.6)
+        u32 sLL = 0, sOF = 0, sML = 0;
+        if (nseq) {
+            u32 hi, lo;
+            KZG_FSE_WINDOW(hi, lo);
+            (void)lo;
+            sLL = __funnelshift_lc(hi, 0u, logLL);
+            const u32 x1 = hi << logLL;
+            sOF = __funnelshift_lc(x1, 0u, logOF);
+            const u32 x2 = x1 << logOF;
+            sML = __funnelshift_lc(x2, 0u, logML);
+            P -= (i32)(logLL + logOF + logML);
+            if (P < lowbits) { nseq = 0; }
+        }
+        const u32 szLL = 1u << logLL, szOF = 1u << logOF, szML = 1u << logML;
+        const u32 kLL = logLL - 31u, kOF = logOF - 31u, kML = logML - 31u;   // nbBits = k + clz(next)
+        u32 lit_end = 0, out_end = 0, ovf = 0;
+        u32 nmax = nseq;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
+
+        for (u32 i0 = 0; i0 < nmax; i0 += KZG_FSE_SERVICE) {
+            {
+                // ring service (warp-uniform point). Chunks issued two service points ago are complete now;
+                // up to 3 new chunks (384 bits >= 4 x 89, the most four sequences can consume) are requested.
+                cp_wait<1>();
+                ready_lo = pend2;
+                const i32 cP = P >> 7;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    if (next_c >= 0 && next_c > cP - KZG_FSE_RING_CHUNKS) {
+                        cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4));
+                        next_c--;
+                    }
+                cp_commit();
+                pend2 = pend1;
+                pend1 = next_c + 1;
+                // lowest chunk the next four sequences can touch: 4 x 89 bits + 64-bit window + 31
+                const i32 need_lo = max((P - 451) >> 7, 0);
+                if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }     // rare: wait for everything
+            }
+#pragma unroll
+            for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
+                const u32 i = i0 + u;
+                if (i < nseq) {
+                    const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
+                    u32 hi, lo;
+                    KZG_FSE_WINDOW(hi, lo);
+                    const u32 ofc = eOF & 63u;
+                    const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
+                    const u32 llb = pLL >> 24, mlb = pML >> 24;
+                    const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
+                    // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
+                    const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
+                    const u32 E = ofc + mlb + llb;
+                    const bool lastseq = i + 1 == nseq;
+                    u32 ofx, mlx_, llx_;
+                    if (E <= 32u) {
+                        ofx = __funnelshift_lc(hi, 0u, ofc);
+                        const u32 t1 = __funnelshift_l(lo, hi, ofc);
+                        mlx_ = __funnelshift_lc(t1, 0u, mlb);
+                        const u32 t2 = __funnelshift_lc(lo, hi, ofc + mlb);
+                        llx_ = __funnelshift_lc(t2, 0u, llb);
+                        const u32 X = __funnelshift_lc(lo, hi, E);
+                        const u32 X2 = X << bLL, X3 = X2 << bML;
+                        if (!lastseq) {
+                            sLL = (nLL << bLL) - szLL + __funnelshift_lc(X, 0u, bLL);
+                            sML = (nML << bML) - szML + __funnelshift_lc(X2, 0u, bML);
+                            sOF = (nOF << bOF) - szOF + __funnelshift_lc(X3, 0u, bOF);
+                        }
+                    } else {
+                        i32 p = P;
+                        ofx = slow_bits(base32, p, ofc); p -= (i32)ofc;
+                        mlx_ = slow_bits(base32, p, mlb); p -= (i32)mlb;
+                        llx_ = slow_bits(base32, p, llb); p -= (i32)llb;
+                        if (!lastseq) {
+                            sLL = (nLL << bLL) - szLL + slow_bits(base32, p, bLL); p -= (i32)bLL;
+                            sML = (nML << bML) - szML + slow_bits(base32, p, bML); p -= (i32)bML;
+                            sOF = (nOF << bOF) - szOF + slow_bits(base32, p, bOF);
+                        }
+                    }
+                    P -= (i32)(E + (lastseq ? 0u : bLL + bML + bOF));
+                    const u32 ofv = (1u << ofc) + ofx;
+                    const u32 ml = (pML & 0xFFFFFFu) + mlx_;
+                    const u32 ll = (pLL & 0xFFFFFFu) + llx_;
+                    // repeat-offset history (Appendix A.6) with selects; only "rep0 - 1" takes a (rare) branch
+                    const bool isrep = ofc < 2u;                         // ofv in {1, 2, 3}
+                    const u32 idx = ofv - 1u + (ll == 0u ? 1u : 0u);     // meaningful when isrep
+                    u32 cand = idx == 1u ? rep1 : rep0;
+                    cand = idx == 2u ? rep2 : cand;
+                    if (isrep && idx == 3u) cand = kzg_rep_dec(rep0);
+                    const u32 off = isrep ? cand : min(ofv - 3u, (u32)KZG_OFF_INVALID);
+                    rep2 = (isrep && idx <= 1u) ? rep2 : rep1;
+                    rep1 = (isrep && idx == 0u) ? rep1 : rep0;
+                    rep0 = off;
+                    lit_end += ll;
+                    out_end += ll + ml;
+                    ovf |= out_end;           // one sequence adds < 2^18, so any overflow past 2^18 leaves a high bit here
+                    out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
+                }
+            }
+        }
+#undef KZG_FSE_WINDOW
+        cp_wait<0>();
+        __syncwarp();
+        if (cb && cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) {
+            // P only decreases, lit_end / out_end only grow: checking the final values covers every step
+            if (nseq && P == lowbits && (ovf >> 18) == 0 && lit_end <= lit_regen && out_end <= block_max) {
+                const u32 regen = out_end + (lit_regen - lit_end);
+                if (regen <= block_max) {
+                    res.status = KZG_OK; res.regen = regen; res.lit_used = lit_end;
+                    res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
+                }
+            }
+            cb->status_seq = res.status;
+            cb->regen = res.regen;
+            cb->lit_used = res.lit_used;
+            cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
+        }
+    }
+}

@@ -16,6 +16,7 @@
 // the reference call ZSTD_decompressStream (kompressor-zstd--nativelib/src/jvmCommonMain/jni/Wrapper.cpp:178).
 #include "kzg_kernels.cuh"
 #include "kzg_stages.cuh"
+#include "kzg_fse.cuh"
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) kzg_scan_kernel(KzgBatch B) {
@@ -78,40 +79,7 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
 }
 
 // ------------------------------------------------------------------------------------------------
-// fse: one thread per block runs the sequential sequence state machine; each thread owns 2560 B of
-// shared memory for its three decode tables (LL 512, ML 512, OF 256 cells of 2 bytes) + 80 B scratch.
-#define KZG_FSE_WARPS 3
-#define KZG_FSE_LANES 29            // blocks per warp: 87 * (2560 + 80) + 384 = 230064 B of the 227 KiB
-#define KZG_FSE_CELLS 1280
-#define KZG_FSE_SCR 40              // u16 per lane
-#define KZG_FSE_SMEM (96 * 4 + KZG_FSE_WARPS * KZG_FSE_LANES * (KZG_FSE_CELLS + KZG_FSE_SCR) * 2)
-__global__ void __launch_bounds__(KZG_FSE_WARPS * 32) kzg_fse_kernel(KzgBatch B) {
-    extern __shared__ uint4 smem4[];
-    u32* llx = reinterpret_cast<u32*>(smem4);      // 36 + 53 packed code entries (+ pad to 96)
-    u32* mlx = llx + 36;
-    u16* scr = reinterpret_cast<u16*>(llx + 96);
-    u16* tabs = scr + KZG_FSE_WARPS * KZG_FSE_LANES * KZG_FSE_SCR;
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 89) llx[threadIdx.x] = B.code_tables[threadIdx.x];
-    __syncthreads();
-    const u32 slot = warp * KZG_FSE_LANES + (lane < KZG_FSE_LANES ? lane : 0);
-    u16* tLL = tabs + (size_t)slot * KZG_FSE_CELLS;
-    u16* tML = tLL + 512;
-    u16* tOF = tLL + 1024;
-    u16* scrLL = scr + (size_t)slot * KZG_FSE_SCR;
-    if (B.ctr->overflow & 3u) return;
-    const u32 n = B.ctr->n_sblocks;
-    for (;;) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(&B.ctr->ticket_fse, 1u);
-        g = __shfl_sync(0xFFFFFFFFu, g, 0);
-        if (g * KZG_FSE_LANES >= n) break;
-        const u32 s = g * KZG_FSE_LANES + lane;
-        if (lane < KZG_FSE_LANES && s < n) kzg_stage_fse_block(B, &B.cblocks[B.slist[s]], tLL, tML, tOF, scrLL, llx, mlx);
-        __syncwarp();
-    }
-}
-
+// fse: see kzg_fse.cuh (one thread per block, lane-interleaved tables, cp.async bitstream ring)
 __global__ void __launch_bounds__(128) kzg_offsets_kernel(KzgBatch B) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n_frames || (B.ctr->overflow & 3u)) return;
