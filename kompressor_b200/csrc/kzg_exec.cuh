@@ -82,16 +82,14 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 kind, u32 sa, const 
     gp += nw << 2;
     while (__any_sync(0xFFFFFFFFu, nw != 0)) {
         if (nw) {
-            u32 hi = lo;
-            if (kind == SRC_TILE) { sa += 4; if (r) hi = lds32(sa); else { hi = 0; } }
-            else if (kind != SRC_FILL) { gw++; if (r) hi = kind == SRC_GLOBAL ? ldg32_hist(gw) : __ldg(gw); }
-            u32 v = __funnelshift_r(lo, hi, r);
-            if (r == 0 && kind != SRC_FILL) {
-                // aligned source: the word just consumed is `lo`; fetch the next one for the next round
-                v = lo;
-                if (nw > 1) hi = kind == SRC_TILE ? lds32(sa) : (kind == SRC_GLOBAL ? ldg32_hist(gw) : __ldg(gw));
-            }
-            sts32(d, v);
+            // `lo` is the aligned source word holding the first byte still to copy; the next aligned word is
+            // fetched only if bytes of it are needed (r != 0) or another destination word follows
+            u32 hi = 0;
+            const bool more = r != 0 || nw > 1;
+            if (kind == SRC_TILE) { sa += 4; if (more) hi = lds32(sa); }
+            else if (kind == SRC_FILL) hi = lo;
+            else { gw++; if (more) hi = kind == SRC_GLOBAL ? ldg32_hist(gw) : __ldg(gw); }
+            sts32(d, __funnelshift_r(lo, hi, r));
             lo = hi;
             d += 4; nw--;
         }
@@ -111,25 +109,24 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 kind, u32 sa, const 
     }
 }
 
-// Warp-cooperative global -> global copy (read-only source), 16-byte vectorised when alignments allow.
+// Warp-cooperative global -> global copy of disjoint ranges, 16-byte vector stores.
+// HIST: the source is output this warp wrote earlier (read at L2); otherwise read-only input data.
+template <bool HIST>
 __device__ __forceinline__ void warp_copy_global(u8* dst, const u8* src, u32 n, u32 lane) {
     const u32 head = min(n, (u32)((16 - ((uintptr_t)dst & 15)) & 15));
-    for (u32 k = lane; k < head; k += 32) dst[k] = src[k];
+    for (u32 k = lane; k < head; k += 32) dst[k] = HIST ? (u8)ldg8_hist(src + k) : src[k];
     dst += head; src += head; n -= head;
     const u32 nvec = n >> 4;
-    if (((uintptr_t)src & 15) == 0) {
-        for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(src)[v];
-    } else {
-        const u32 r = (u32)((uintptr_t)src & 3) * 8;
-        const u32* sw = reinterpret_cast<const u32*>(src - ((uintptr_t)src & 3));
-        for (u32 v = lane; v < nvec; v += 32) {
-            const u32 a = sw[4 * v], b = sw[4 * v + 1], c = sw[4 * v + 2], d = sw[4 * v + 3];
-            const u32 e = r ? sw[4 * v + 4] : 0u;
-            reinterpret_cast<uint4*>(dst)[v] = make_uint4(__funnelshift_r(a, b, r), __funnelshift_r(b, c, r),
-                                                          __funnelshift_r(c, d, r), __funnelshift_r(d, e, r));
-        }
+    const u32 r = (u32)((uintptr_t)src & 3) * 8;
+    const u32* sw = reinterpret_cast<const u32*>(src - ((uintptr_t)src & 3));
+    for (u32 v = lane; v < nvec; v += 32) {
+        u32 a, b, c, d, e = 0;
+        if (HIST) { a = ldg32_hist(sw + 4 * v); b = ldg32_hist(sw + 4 * v + 1); c = ldg32_hist(sw + 4 * v + 2); d = ldg32_hist(sw + 4 * v + 3); if (r) e = ldg32_hist(sw + 4 * v + 4); }
+        else { a = sw[4 * v]; b = sw[4 * v + 1]; c = sw[4 * v + 2]; d = sw[4 * v + 3]; if (r) e = sw[4 * v + 4]; }
+        reinterpret_cast<uint4*>(dst)[v] = make_uint4(__funnelshift_r(a, b, r), __funnelshift_r(b, c, r),
+                                                      __funnelshift_r(c, d, r), __funnelshift_r(d, e, r));
     }
-    for (u32 k = (nvec << 4) + lane; k < n; k += 32) dst[k] = src[k];
+    for (u32 k = (nvec << 4) + lane; k < n; k += 32) dst[k] = HIST ? (u8)ldg8_hist(src + k) : src[k];
 }
 
 __device__ __forceinline__ void warp_set_global(u8* dst, u32 byte, u32 n, u32 lane) {
@@ -202,7 +199,7 @@ __device__ __forceinline__ void slide(Win& w, i32 cur, u32 lane) {
 }  // namespace kzg_ex
 
 // Executes one compressed block with sequences. Returns true (uniformly) if the block is corrupt.
-__device__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const KzgCBlock* cb, u8* out, u32 tile, u32 lane) {
+__device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const KzgCBlock* cb, u8* out, u32 tile, u32 lane) {
     using namespace kzg_ex;
     const u32 nseq = cb->n_seq, lit_regen = cb->lit_regen, lit_type = cb->lit_type;
     const u8* lit = lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
@@ -314,34 +311,13 @@ __device__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const
                 __syncwarp();
                 u8* d = out + l_poe;
                 if (lit_type == 1) warp_set_global(d, rle, l_ll, lane);
-                else warp_copy_global(d, lit + l_ple, l_ll, lane);
+                else warp_copy_global<false>(d, lit + l_ple, l_ll, lane);
                 __threadfence_block();
                 __syncwarp();
                 d += l_ll;
                 const i32 sp = (i32)(l_poe + l_ll) - (i32)l_off;
-                if (l_off >= l_ml && w.boff + sp >= 0 && l_off >= 16) {
-                    // disjoint source inside the frame: chunks of 512 bytes, loads before stores per chunk
-                    const u8* s = out + sp;
-                    for (u32 k0 = 0; k0 < l_ml; k0 += 512) {
-                        const u32 k = k0 + (lane << 4);
-                        if (k + 16 <= l_ml) {
-                            uint4 v;
-                            u8 tmp[16];
-#pragma unroll
-                            for (int q = 0; q < 16; q++) tmp[q] = (u8)ldg8_hist(s + k + q);
-                            v.x = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((u32)tmp[3] << 24);
-                            v.y = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((u32)tmp[7] << 24);
-                            v.z = tmp[8] | (tmp[9] << 8) | (tmp[10] << 16) | ((u32)tmp[11] << 24);
-                            v.w = tmp[12] | (tmp[13] << 8) | (tmp[14] << 16) | ((u32)tmp[15] << 24);
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const u32 x = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
-                                d[k + 4 * q] = (u8)x; d[k + 4 * q + 1] = (u8)(x >> 8); d[k + 4 * q + 2] = (u8)(x >> 16); d[k + 4 * q + 3] = (u8)(x >> 24);
-                            }
-                        } else {
-                            for (u32 q = k; q < l_ml && q < k + 16; q++) d[q] = (u8)ldg8_hist(s + q);
-                        }
-                    }
+                if (l_off >= l_ml && w.boff + sp >= 0) {
+                    warp_copy_global<true>(d, out + sp, l_ml, lane);      // disjoint source inside the frame
                 } else {
                     // overlapping (period l_off) or reaching into the dictionary: every byte equals one of the
                     // l_off bytes just before the match, all of which are final
@@ -369,7 +345,7 @@ __device__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const
         const u32 used = (u32)(carry >> 28) & 0x3FFFFu;
         if (lit_regen > used) {
             if (lit_type == 1) warp_set_global(out + cur, rle, lit_regen - used, lane);
-            else warp_copy_global(out + cur, lit + used, lit_regen - used, lane);
+            else warp_copy_global<false>(out + cur, lit + used, lit_regen - used, lane);
         }
     }
     __threadfence_block();
@@ -396,14 +372,14 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32) kzg_exec_kernel(KzgBatch B)
         for (u32 k = 0; k < nblk && !failed; k++) {
             const KzgBlock blk = B.blocks[first + k];
             u8* out = fdst + blk.out_off;
-            if (blk.type == 0) warp_copy_global(out, B.src + blk.src, blk.regen, lane);
+            if (blk.type == 0) warp_copy_global<false>(out, B.src + blk.src, blk.regen, lane);
             else if (blk.type == 1) warp_set_global(out, B.src[blk.src], blk.regen, lane);
             else {
                 const KzgCBlock* cb = &B.cblocks[blk.cidx];
                 if (cb->n_seq == 0) {
                     const u8* lit = cb->lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
                     if (cb->lit_type == 1) warp_set_global(out, lit[0], blk.regen, lane);
-                    else warp_copy_global(out, lit, blk.regen, lane);
+                    else warp_copy_global<false>(out, lit, blk.regen, lane);
                 } else failed = kzg_exec_sequences(B, blk, cb, out, tile, lane);
             }
             __threadfence_block();

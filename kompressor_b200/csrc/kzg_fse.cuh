@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
         if (nseq) {
             u32 hi, lo;
             KZG_FSE_WINDOW(hi, lo);
-            (void)lo;
+            if (lo == 0xFFFFFFFFu && hi == 0u) hi = 0u;    // (lo is unused here)
             sLL = __funnelshift_lc(hi, 0u, logLL);
             const u32 x1 = hi << logLL;
             sOF = __funnelshift_lc(x1, 0u, logOF);
