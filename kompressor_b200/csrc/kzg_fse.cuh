@@ -28,6 +28,9 @@
 #define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_WARPS * (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES))
 #define KZG_FSE_SERVICE 4                                   // sequences between ring service points
+#ifndef KZG_FSE_WIDE_LIMIT
+#define KZG_FSE_WIDE_LIMIT 32u                               // most extra bits per sequence the fast loop extracts (tests lower it)
+#endif
 
 namespace kzg_fse {
 
@@ -84,7 +87,7 @@ __device__ __forceinline__ u32 build_table(u32 tab, u32 ring, const KzgFseDesc* 
 }
 
 // Generic (slow, rare) backward bit read straight from global memory: n <= 32 bits below position P.
-__device__ __noinline__ u32 slow_bits(const u32* base32, i32 P, u32 n) {
+__device__ __forceinline__ u32 slow_bits(const u32* base32, i32 P, u32 n) {
     if (n == 0) return 0;
     const i32 k = P >> 5;
     const u32 q = (u32)P & 31u;
@@ -93,6 +96,74 @@ __device__ __noinline__ u32 slow_bits(const u32* base32, i32 P, u32 n) {
 }
 
 struct Result { u32 status, regen, lit_used, rep0, rep1, rep2; };
+
+// Per-block decode parameters shared by the fast loop and the general fallback.
+struct Job {
+    const u32* base32;      // 16-byte aligned chunk holding the first byte of the bitstream
+    u64* out;               // sequence records
+    i32 P0, lowbits;        // bit position above the first unread bit / of the stream's first bit
+    u32 nseq, lit_regen, block_max;
+    u32 logLL, logOF, logML;
+    u32 rep0, rep1, rep2;   // encoded repeat offsets at block start
+};
+
+__device__ __forceinline__ void finish_result(Result& res, const Job& j, i32 P, u32 lit_end, u32 out_end, u32 ovf,
+                                              u32 rep0, u32 rep1, u32 rep2) {
+    // P only decreases, lit_end / out_end only grow: checking the final values covers every step.
+    if (P == j.lowbits && (ovf >> 18) == 0 && lit_end <= j.lit_regen && out_end <= j.block_max) {
+        const u32 regen = out_end + (j.lit_regen - lit_end);
+        if (regen <= j.block_max) {
+            res.status = KZG_OK; res.regen = regen; res.lit_used = lit_end;
+            res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
+        }
+    }
+}
+
+// General decoder for one block: any field widths (up to 89 bits per sequence), bits read from global
+// memory.  Only used for blocks whose sequences carry more than 32 extra bits at once, which the fast
+// loop does not handle; one lane runs it after the fast loop, so speed does not matter.
+__device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF, u32 s_llx, u32 s_mlx, Result& res) {
+    i32 P = j.P0;
+    u32 sLL = slow_bits(j.base32, P, j.logLL); P -= (i32)j.logLL;
+    u32 sOF = slow_bits(j.base32, P, j.logOF); P -= (i32)j.logOF;
+    u32 sML = slow_bits(j.base32, P, j.logML); P -= (i32)j.logML;
+    if (P < j.lowbits) return;
+    u32 rep0 = j.rep0, rep1 = j.rep1, rep2 = j.rep2, lit_end = 0, out_end = 0, ovf = 0;
+    for (u32 i = 0; i < j.nseq; i++) {
+        const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
+        const u32 ofc = eOF & 63u;
+        const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
+        const u32 ofv = (1u << ofc) + slow_bits(j.base32, P, ofc); P -= (i32)ofc;
+        const u32 ml = (pML & 0xFFFFFFu) + slow_bits(j.base32, P, pML >> 24); P -= (i32)(pML >> 24);
+        const u32 ll = (pLL & 0xFFFFFFu) + slow_bits(j.base32, P, pLL >> 24); P -= (i32)(pLL >> 24);
+        u32 off;
+        if (ofv > 3) {
+            off = min(ofv - 3u, (u32)KZG_OFF_INVALID);
+            rep2 = rep1; rep1 = rep0; rep0 = off;
+        } else {
+            const u32 idx = ofv - 1 + (ll == 0);
+            if (idx == 0) off = rep0;
+            else {
+                off = idx == 3 ? kzg_rep_dec(rep0) : (idx == 1 ? rep1 : rep2);
+                if (idx != 1) rep2 = rep1;
+                rep1 = rep0; rep0 = off;
+            }
+        }
+        lit_end += ll;
+        out_end += ll + ml;
+        ovf |= out_end;
+        j.out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
+        if (i + 1 < j.nseq) {
+            const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
+            const u32 bLL = j.logLL - (u32)kzg_highbit(nLL), bML = j.logML - (u32)kzg_highbit(nML), bOF = j.logOF - (u32)kzg_highbit(nOF);
+            sLL = (nLL << bLL) - (1u << j.logLL) + slow_bits(j.base32, P, bLL); P -= (i32)bLL;
+            sML = (nML << bML) - (1u << j.logML) + slow_bits(j.base32, P, bML); P -= (i32)bML;
+            sOF = (nOF << bOF) - (1u << j.logOF) + slow_bits(j.base32, P, bOF); P -= (i32)bOF;
+        }
+        if (P < j.lowbits) return;
+    }
+    finish_result(res, j, P, lit_end, out_end, ovf, rep0, rep1, rep2);
+}
 
 }  // namespace kzg_fse
 
@@ -118,43 +189,44 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
         if (g * 32 >= n) break;
         const u32 si = g * 32 + lane;
         KzgCBlock* cb = nullptr;
-        u32 nseq = 0;
+        Job j;
+        j.base32 = nullptr; j.out = nullptr; j.P0 = 0; j.lowbits = 0; j.nseq = 0; j.lit_regen = 0; j.block_max = 0;
+        j.logLL = j.logOF = j.logML = 0;
+        j.rep0 = 1; j.rep1 = 4; j.rep2 = 8;
         if (si < n) {
             cb = &B.cblocks[B.slist[si]];
-            if (cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) nseq = cb->n_seq;
+            if (cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) j.nseq = cb->n_seq;
         }
-        // ---- tables (per lane, in its own column; the ring doubles as build scratch)
-        u32 logLL = 0, logOF = 0, logML = 0;
-        if (nseq) {
+        // ---- tables (per lane, in its own column; the ring doubles as build scratch).  Idle lanes get
+        // one-cell tables so that the branch-free loop below stays in bounds for them too.
+        if (j.nseq) {
             const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-            logLL = build_table(tLL, s_ring, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
-            logOF = build_table(tOF, s_ring, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
-            logML = build_table(tML, s_ring, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
-        }
+            j.logLL = build_table(tLL, s_ring, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
+            j.logOF = build_table(tOF, s_ring, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
+            j.logML = build_table(tML, s_ring, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
+        } else { sts16(tLL, 1u << 6); sts16(tOF, 1u << 6); sts16(tML, 1u << 6); }
         __syncwarp();
         // ---- bitstream set-up
         Result res;
         res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;
-        u32 rep0 = 1, rep1 = 4, rep2 = 8;
-        if (nseq && !cb->first_in_frame) { rep0 = KZG_OFF_SYM | 0; rep1 = KZG_OFF_SYM | 1; rep2 = KZG_OFF_SYM | 2; }
-        res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
+        if (j.nseq && !cb->first_in_frame) { j.rep0 = KZG_OFF_SYM | 0; j.rep1 = KZG_OFF_SYM | 1; j.rep2 = KZG_OFF_SYM | 2; }
+        res.rep0 = j.rep0; res.rep1 = j.rep1; res.rep2 = j.rep2;
         const u8* base = nullptr;
-        i32 P = 0, lowbits = 0, next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
-        u64* out = nullptr;
-        u32 lit_regen = 0, block_max = 0;
-        if (nseq) {
+        i32 next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
+        if (j.nseq) {
             const u8* start = B.src + cb->src + cb->seq_src;
             const u32 size = cb->seq_size;
             const u32 last = size ? start[size - 1] : 0u;
-            if (last == 0) nseq = 0;                       // no padding marker: corrupt (status stays CORRUPTION)
+            if (last == 0) j.nseq = 0;                     // no padding marker: corrupt (status stays CORRUPTION)
             else {
                 base = (const u8*)((uintptr_t)start & ~(uintptr_t)15);
-                lowbits = (i32)(8u * (u32)(start - base));
-                P = lowbits + (i32)(8u * (size - 1)) + kzg_highbit(last);
-                out = B.seq_pool + cb->seq_out;
-                lit_regen = cb->lit_regen;
-                block_max = B.frames[cb->frame].block_max;
-                next_c = P >> 7;
+                j.base32 = reinterpret_cast<const u32*>(base);
+                j.lowbits = (i32)(8u * (u32)(start - base));
+                j.P0 = j.lowbits + (i32)(8u * (size - 1)) + kzg_highbit(last);
+                j.out = B.seq_pool + cb->seq_out;
+                j.lit_regen = cb->lit_regen;
+                j.block_max = B.frames[cb->frame].block_max;
+                next_c = j.P0 >> 7;
                 for (int r = 0; r < KZG_FSE_RING_CHUNKS; r++)
                     if (next_c >= 0) { cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4)); next_c--; }
             }
@@ -162,7 +234,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
         cp_commit();
         cp_wait<0>();
         ready_lo = pend1 = pend2 = next_c + 1;
-        const u32* base32 = reinterpret_cast<const u32*>(base);
+        i32 P = j.P0;
 
         // 64-bit window [P-64, P) -> hi:lo from the lane's ring (word w of the stream sits at (w & 31) * 4)
 #define KZG_FSE_WINDOW(hi, lo)                                                     \
@@ -177,25 +249,31 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
 
         // ---- initial states: LL, OF, ML (Appendix A.6)
         u32 sLL = 0, sOF = 0, sML = 0;
+        u32 nseq = j.nseq;
         if (nseq) {
             u32 hi, lo;
             KZG_FSE_WINDOW(hi, lo);
             if (lo == 0xFFFFFFFFu && hi == 0u) hi = 0u;    // (lo is unused here)
-            sLL = __funnelshift_lc(hi, 0u, logLL);
-            const u32 x1 = hi << logLL;
-            sOF = __funnelshift_lc(x1, 0u, logOF);
-            const u32 x2 = x1 << logOF;
-            sML = __funnelshift_lc(x2, 0u, logML);
-            P -= (i32)(logLL + logOF + logML);
-            if (P < lowbits) { nseq = 0; }
+            sLL = __funnelshift_lc(hi, 0u, j.logLL);
+            const u32 x1 = hi << j.logLL;
+            sOF = __funnelshift_lc(x1, 0u, j.logOF);
+            const u32 x2 = x1 << j.logOF;
+            sML = __funnelshift_lc(x2, 0u, j.logML);
+            P -= (i32)(j.logLL + j.logOF + j.logML);
+            if (P < j.lowbits) nseq = 0;
         }
-        const u32 szLL = 1u << logLL, szOF = 1u << logOF, szML = 1u << logML;
-        const u32 kLL = logLL - 31u, kOF = logOF - 31u, kML = logML - 31u;   // nbBits = k + clz(next)
+        const u32 szLL = 1u << j.logLL, szOF = 1u << j.logOF, szML = 1u << j.logML;
+        const u32 kLL = j.logLL - 31u, kOF = j.logOF - 31u, kML = j.logML - 31u;   // nbBits = k + clz(next)
+        u32 rep0 = j.rep0, rep1 = j.rep1, rep2 = j.rep2;
         u32 lit_end = 0, out_end = 0, ovf = 0;
+        bool wide = false;                       // a sequence with more than 32 extra bits was seen
+        u64* out = j.out;
         u32 nmax = nseq;
 #pragma unroll
         for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
 
+        // The loop body is straight-line code: lanes that ran out of sequences keep computing on frozen
+        // positions (their stores, bit consumption and history updates are masked off).
         for (u32 i0 = 0; i0 < nmax; i0 += KZG_FSE_SERVICE) {
             {
                 // ring service (warp-uniform point). Chunks issued two service points ago are complete now;
@@ -219,80 +297,62 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
 #pragma unroll
             for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
                 const u32 i = i0 + u;
-                if (i < nseq) {
-                    const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
-                    u32 hi, lo;
-                    KZG_FSE_WINDOW(hi, lo);
-                    const u32 ofc = eOF & 63u;
-                    const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
-                    const u32 llb = pLL >> 24, mlb = pML >> 24;
-                    const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
-                    // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
-                    const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
-                    const u32 E = ofc + mlb + llb;
-                    const bool lastseq = i + 1 == nseq;
-                    u32 ofx, mlx_, llx_;
-                    if (E <= 32u) {
-                        ofx = __funnelshift_lc(hi, 0u, ofc);
-                        const u32 t1 = __funnelshift_l(lo, hi, ofc);
-                        mlx_ = __funnelshift_lc(t1, 0u, mlb);
-                        const u32 t2 = __funnelshift_lc(lo, hi, ofc + mlb);
-                        llx_ = __funnelshift_lc(t2, 0u, llb);
-                        const u32 X = __funnelshift_lc(lo, hi, E);
-                        const u32 X2 = X << bLL, X3 = X2 << bML;
-                        if (!lastseq) {
-                            sLL = (nLL << bLL) - szLL + __funnelshift_lc(X, 0u, bLL);
-                            sML = (nML << bML) - szML + __funnelshift_lc(X2, 0u, bML);
-                            sOF = (nOF << bOF) - szOF + __funnelshift_lc(X3, 0u, bOF);
-                        }
-                    } else {
-                        i32 p = P;
-                        ofx = slow_bits(base32, p, ofc); p -= (i32)ofc;
-                        mlx_ = slow_bits(base32, p, mlb); p -= (i32)mlb;
-                        llx_ = slow_bits(base32, p, llb); p -= (i32)llb;
-                        if (!lastseq) {
-                            sLL = (nLL << bLL) - szLL + slow_bits(base32, p, bLL); p -= (i32)bLL;
-                            sML = (nML << bML) - szML + slow_bits(base32, p, bML); p -= (i32)bML;
-                            sOF = (nOF << bOF) - szOF + slow_bits(base32, p, bOF);
-                        }
-                    }
-                    P -= (i32)(E + (lastseq ? 0u : bLL + bML + bOF));
-                    const u32 ofv = (1u << ofc) + ofx;
-                    const u32 ml = (pML & 0xFFFFFFu) + mlx_;
-                    const u32 ll = (pLL & 0xFFFFFFu) + llx_;
-                    // repeat-offset history (Appendix A.6) with selects; only "rep0 - 1" takes a (rare) branch
-                    const bool isrep = ofc < 2u;                         // ofv in {1, 2, 3}
-                    const u32 idx = ofv - 1u + (ll == 0u ? 1u : 0u);     // meaningful when isrep
-                    u32 cand = idx == 1u ? rep1 : rep0;
-                    cand = idx == 2u ? rep2 : cand;
-                    if (isrep && idx == 3u) cand = kzg_rep_dec(rep0);
-                    const u32 off = isrep ? cand : min(ofv - 3u, (u32)KZG_OFF_INVALID);
-                    rep2 = (isrep && idx <= 1u) ? rep2 : rep1;
-                    rep1 = (isrep && idx == 0u) ? rep1 : rep0;
-                    rep0 = off;
-                    lit_end += ll;
-                    out_end += ll + ml;
-                    ovf |= out_end;           // one sequence adds < 2^18, so any overflow past 2^18 leaves a high bit here
-                    out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
-                }
+                const bool act = i < nseq, notlast = i + 1 < nseq;
+                const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
+                u32 hi, lo;
+                KZG_FSE_WINDOW(hi, lo);
+                const u32 ofc = eOF & 63u;
+                const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
+                const u32 llb = pLL >> 24, mlb = pML >> 24;
+                const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
+                // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
+                const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
+                const u32 E = ofc + mlb + llb;
+                wide |= act && E > KZG_FSE_WIDE_LIMIT;
+                // all six fields straight out of the 64-bit window (valid when E <= 32: E + 26 <= 58 bits)
+                const u32 ofx = __funnelshift_lc(hi, 0u, ofc);
+                const u32 mlx_ = __funnelshift_lc(__funnelshift_l(lo, hi, ofc), 0u, mlb);
+                const u32 llx_ = __funnelshift_lc(__funnelshift_lc(lo, hi, ofc + mlb), 0u, llb);
+                const u32 X = __funnelshift_lc(lo, hi, E);
+                const u32 X2 = X << bLL, X3 = X2 << bML;
+                sLL = (nLL << bLL) - szLL + __funnelshift_lc(X, 0u, bLL);
+                sML = (nML << bML) - szML + __funnelshift_lc(X2, 0u, bML);
+                sOF = (nOF << bOF) - szOF + __funnelshift_lc(X3, 0u, bOF);
+                P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
+                const u32 ofv = (1u << ofc) + ofx;
+                const u32 ml = act ? (pML & 0xFFFFFFu) + mlx_ : 0u;
+                const u32 ll = act ? (pLL & 0xFFFFFFu) + llx_ : 0u;
+                // repeat-offset history (Appendix A.6) with selects.  "rep0 - 1": a symbolic value counts its
+                // decrement in bits [2,27) (+4), a concrete one just loses 1 (0 is rejected at execution).
+                const bool isrep = ofc < 2u;                         // ofv in {1, 2, 3}
+                const u32 idx = ofv - 1u + (ll == 0u ? 1u : 0u);     // meaningful when isrep
+                const u32 dec = rep0 - 1u + (rep0 >> 27) * 5u;
+                u32 cand = idx == 1u ? rep1 : rep0;
+                cand = idx == 2u ? rep2 : cand;
+                cand = idx == 3u ? dec : cand;
+                const u32 off = isrep ? cand : min(ofv - 3u, (u32)KZG_OFF_INVALID);
+                rep2 = ((isrep && idx <= 1u) || !act) ? rep2 : rep1;
+                rep1 = ((isrep && idx == 0u) || !act) ? rep1 : rep0;
+                rep0 = act ? off : rep0;
+                lit_end += ll;
+                out_end += ll + ml;
+                ovf |= out_end;           // one sequence adds < 2^18, so any overflow past 2^18 leaves a high bit here
+                if (act) out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
             }
         }
 #undef KZG_FSE_WINDOW
         cp_wait<0>();
         __syncwarp();
         if (cb && cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) {
-            // P only decreases, lit_end / out_end only grow: checking the final values covers every step
-            if (nseq && P == lowbits && (ovf >> 18) == 0 && lit_end <= lit_regen && out_end <= block_max) {
-                const u32 regen = out_end + (lit_regen - lit_end);
-                if (regen <= block_max) {
-                    res.status = KZG_OK; res.regen = regen; res.lit_used = lit_end;
-                    res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
-                }
+            if (nseq) {
+                if (wide) slow_decode(j, tLL, tML, tOF, s_llx, s_mlx, res);
+                else finish_result(res, j, P, lit_end, out_end, ovf, rep0, rep1, rep2);
             }
             cb->status_seq = res.status;
             cb->regen = res.regen;
             cb->lit_used = res.lit_used;
             cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
         }
+        __syncwarp();
     }
 }

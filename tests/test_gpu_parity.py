@@ -103,6 +103,20 @@ def test_run_like_data_overlapping_matches(dec, libzstd):
     assert outs == [r for r in raws for _ in range(3)]
 
 
+def test_far_offsets_and_wide_sequences(dec, libzstd):
+    """8 MiB window (level 19, streamed header): matches millions of bytes back, literal runs and matches
+    of 64 KiB+ in one sequence (more than 32 extra bits per sequence: the sequence kernel's general path)."""
+    rng = np.random.default_rng(21)
+    a = rng.integers(0, 256, 5 << 20, dtype=np.uint8).tobytes()
+    b = rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()
+    raw = a + b + a[1000:121000] + b[:3] + a[4 << 20:(4 << 20) + 70000] + b + a[77:131149]
+    frames = [libzstd.compress(raw, 19, checksum=True, pledged=p) for p in (True, False)]
+    outs, status, _ = run(dec, frames, [len(raw)] * len(frames))
+    assert (status == 0).all()
+    for o in outs:
+        assert hashlib.sha256(o).digest() == hashlib.sha256(raw).digest()
+
+
 def test_unaligned_output_offsets(dec, libzstd):
     import corpus
     raws = [bytes(corpus.generate("logs", 90 + i, 30000 + 17 * i)) for i in range(9)]
