@@ -7,10 +7,13 @@
 //   * the window covers output positions [T0, T0 + KZG_EX_TILE) of the current block; after every batch
 //     the completed 16-byte chunks are flushed, and when the window is full it slides, keeping the last
 //     KZG_EX_KEEP bytes as near history;
-//   * a match whose source is still inside the window is copied shared -> shared; older history (earlier
-//     in the block, earlier blocks of the frame, the dictionary) is read back from global memory / L2,
-//     which this warp itself wrote and flushed earlier;
-//   * copies are word-granular (aligned 32-bit loads + funnel shift), bytes only at the ragged ends;
+//   * every global read on the hot path is a cp.async (LDGSTS) into shared-memory staging, so no lane
+//     ever waits on a load register: the literal bytes of a batch are contiguous in the literal stream
+//     and are staged as 16-byte chunks one batch ahead; a match whose source has already left the window
+//     (earlier in the block, earlier blocks of the frame: data this warp flushed to HBM/L2 before) stages
+//     the 16-byte chunks covering its source, issued before the batch's literal pass and consumed after it;
+//   * all per-lane copies are then shared -> shared, word-granular (aligned 32-bit loads + funnel shift),
+//     bytes only at the ragged ends, with warp-uniform trip counts;
 //   * matches whose source overlaps output produced by earlier lanes of the same batch wait for those
 //     lanes: the batch is resolved in rounds, each round completing every lane whose source lies below
 //     the first still-pending lane (usually one round);
@@ -21,10 +24,15 @@
 #include "kzg_stages.cuh"
 
 #define KZG_EX_WARPS 4
-#define KZG_EX_TILE 8192u
-#define KZG_EX_KEEP 4032u           // multiple of 16; TILE - KEEP - 16 >= 32 * 2 * KZG_EX_LONG
-#define KZG_EX_LONG 64u
-#define KZG_EX_SMEM (KZG_EX_WARPS * KZG_EX_TILE)
+#define KZG_EX_TILE 4096u
+#define KZG_EX_KEEP 1024u           // flushed history kept in the window after a slide (multiple of 16)
+#define KZG_EX_CAP (KZG_EX_TILE - KZG_EX_KEEP - 32u)   // most output one group of lanes may span
+#define KZG_EX_LONG 64u             // literal runs / matches longer than this are copied by the whole warp
+#define KZG_EX_LITSTAGE 1024u       // most literal bytes of one batch that are staged (else read directly)
+#define KZG_EX_LIT_BYTES (KZG_EX_LITSTAGE + 32u)
+#define KZG_EX_MSTAGE 80u           // per-lane match staging: the 16-byte chunks covering <= 64 source bytes
+#define KZG_EX_WARP_SMEM (KZG_EX_TILE + KZG_EX_LIT_BYTES + 32u * KZG_EX_MSTAGE)
+#define KZG_EX_SMEM (KZG_EX_WARPS * KZG_EX_WARP_SMEM + 16u)
 
 namespace kzg_ex {
 
@@ -40,73 +48,45 @@ __device__ __forceinline__ uint4 lds128(u32 a) {
 __device__ __forceinline__ void sts128(u32 a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 // History written earlier by this warp: read at L2 (the coherence point), never from a stale L1 line.
 __device__ __forceinline__ u32 ldg32_hist(const u32* p) { return __ldcg(p); }
 __device__ __forceinline__ u32 ldg8_hist(const u8* p) { return (u32)__ldcg(p); }
 
-// Source of a per-lane copy into the window.
-enum : u32 { SRC_TILE = 0, SRC_GLOBAL = 1, SRC_CONST = 2, SRC_FILL = 3 };
-
-// One lane copies n (<= KZG_EX_LONG) bytes to shared address `d`.  kind selects where the bytes come from:
-//   SRC_TILE   shared address `sa` (window -> window, source at least 8 bytes behind the destination)
-//   SRC_GLOBAL history at `gp`, re-read from L2          SRC_CONST  read-only data at `gp` (literals)
-//   SRC_FILL   the byte `fill`
-// Every lane of the warp calls this together (n = 0 for idle lanes): three uniform loops, no syncs.
-__device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 kind, u32 sa, const u8* gp, u32 fill) {
-    // head: bytes until the destination is word aligned
-    u32 h = min(n, (4u - (d & 3u)) & 3u);
-    n -= h;
-    while (__any_sync(0xFFFFFFFFu, h != 0)) {
-        if (h) {
-            u32 v;
-            if (kind == SRC_TILE) v = lds8(sa);
-            else if (kind == SRC_GLOBAL) v = ldg8_hist(gp);
-            else if (kind == SRC_CONST) v = __ldg(gp);
-            else v = fill;
-            sts8(d, v);
-            d++; sa++; gp++; h--;
-        }
-    }
-    // words
-    u32 nw = n >> 2;
-    n &= 3u;
-    u32 r = 0, lo = 0;
-    const u32* gw = nullptr;
-    if (kind == SRC_TILE) { r = (sa & 3u) * 8u; sa &= ~3u; if (nw) lo = lds32(sa); }
-    else if (kind == SRC_FILL) { lo = fill * 0x01010101u; }
-    else {
-        r = (u32)((uintptr_t)gp & 3u) * 8u;
-        gw = reinterpret_cast<const u32*>(gp - ((uintptr_t)gp & 3u));
-        if (nw) lo = kind == SRC_GLOBAL ? ldg32_hist(gw) : __ldg(gw);
-    }
-    gp += nw << 2;
-    while (__any_sync(0xFFFFFFFFu, nw != 0)) {
-        if (nw) {
+// One lane copies n (<= KZG_EX_LONG) bytes from shared address `sa` to shared address `d` (fill: the byte
+// `fillv` instead).  Source and destination may be unaligned; a window -> window source must be at least
+// 8 bytes behind its destination.  Every lane of the warp calls this together (n = 0 for idle lanes): the
+// word loop runs the warp's largest trip count, nothing else loops.
+__device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 fillv) {
+    const u32 h = min(n, (0u - d) & 3u);
+#pragma unroll
+    for (u32 k = 0; k < 3; k++)
+        if (k < h) sts8(d + k, fill ? fillv : lds8(sa + k));
+    d += h; sa += h; n -= h;
+    const u32 nw = n >> 2, t = n & 3u;
+    const u32 r = (sa & 3u) * 8u;
+    u32 A = sa & ~3u;
+    u32 lo = fill ? fillv * 0x01010101u : (nw ? lds32(A) : 0u);
+    const u32 maxw = __reduce_max_sync(0xFFFFFFFFu, nw);
+    for (u32 k = 0; k < maxw; k++) {
+        if (k < nw) {
             // `lo` is the aligned source word holding the first byte still to copy; the next aligned word is
             // fetched only if bytes of it are needed (r != 0) or another destination word follows
-            u32 hi = 0;
-            const bool more = r != 0 || nw > 1;
-            if (kind == SRC_TILE) { sa += 4; if (more) hi = lds32(sa); }
-            else if (kind == SRC_FILL) hi = lo;
-            else { gw++; if (more) hi = kind == SRC_GLOBAL ? ldg32_hist(gw) : __ldg(gw); }
+            u32 hi = lo;
+            if (!fill) { A += 4; hi = (r != 0 || k + 1 < nw) ? lds32(A) : 0u; }
             sts32(d, __funnelshift_r(lo, hi, r));
             lo = hi;
-            d += 4; nw--;
+            d += 4;
         }
     }
-    // tail bytes
-    if (kind == SRC_TILE) sa += (r >> 3);           // back to a byte address
-    while (__any_sync(0xFFFFFFFFu, n != 0)) {
-        if (n) {
-            u32 v;
-            if (kind == SRC_TILE) v = lds8(sa);
-            else if (kind == SRC_GLOBAL) v = ldg8_hist(gp);
-            else if (kind == SRC_CONST) v = __ldg(gp);
-            else v = fill;
-            sts8(d, v);
-            d++; sa++; gp++; n--;
-        }
-    }
+    const u32 ta = sa + (nw << 2);
+#pragma unroll
+    for (u32 k = 0; k < 3; k++)
+        if (k < t) sts8(d + k, fill ? fillv : lds8(ta + k));
 }
 
 // Warp-cooperative global -> global copy of disjoint ranges, 16-byte vector stores.
@@ -177,8 +157,8 @@ __device__ __forceinline__ void flush(Win& w, i32 upto, bool all, u32 lane) {
     }
 }
 
-// Makes room so that positions up to `need_end` fit: slides the window down, keeping KZG_EX_KEEP bytes of
-// flushed history.  Requires everything below `cur` (rounded down to 16) to be flushed already.
+// Slides the window down, keeping KZG_EX_KEEP bytes of flushed history below w.F.
+// Requires everything below `cur` (rounded down to 16) to be flushed already.
 __device__ __forceinline__ void slide(Win& w, i32 cur, u32 lane) {
     i32 nT0 = w.F - (i32)KZG_EX_KEEP;
     if (nT0 <= w.T0) return;
@@ -196,20 +176,37 @@ __device__ __forceinline__ void slide(Win& w, i32 cur, u32 lane) {
     if (w.Tv < nT0) w.Tv = nT0;
 }
 
+// Literal staging: the 16-byte chunks covering literal-stream bytes [l0, l1) are copied (asynchronously)
+// to `stage`; byte l of the stream then sits at stage + (l - l0) + ((lit + l0) & 15).
+// Returns false (nothing issued) if the range is too large to stage.
+__device__ __forceinline__ bool stage_literals(u32 stage, const u8* lit, u32 l0, u32 l1, u32 lane) {
+    if (l1 - l0 > KZG_EX_LITSTAGE) return false;
+    const u8* g0 = lit + l0;
+    const u32 a = (u32)((uintptr_t)g0 & 15);
+    const u32 nch = (a + (l1 - l0) + 15u) >> 4;             // <= 66
+    g0 -= a;
+    for (u32 c = lane; c < nch; c += 32) cp_async16(stage + (c << 4), g0 + ((size_t)c << 4));
+    return true;
+}
+
 }  // namespace kzg_ex
 
 // Executes one compressed block with sequences. Returns true (uniformly) if the block is corrupt.
-__device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const KzgCBlock* cb, u8* out, u32 tile, u32 lane) {
+// smem: this warp's shared memory (window | literal staging | match staging).
+__device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const KzgCBlock* cb, u8* out,
+                                                   u32 smem, u32 lane) {
     using namespace kzg_ex;
     const u32 nseq = cb->n_seq, lit_regen = cb->lit_regen, lit_type = cb->lit_type;
     const u8* lit = lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
-    const u32 rle = lit_type == 1 ? (u32)lit[0] : 0u;
-    const u32 lkind = lit_type == 1 ? SRC_FILL : SRC_CONST;
+    const bool lfill = lit_type == 1;
+    const u32 rle = lfill ? (u32)lit[0] : 0u;
     const u64* seqs = B.seq_pool + cb->seq_out;
     const u32 ri0 = cb->rep_init[0], ri1 = cb->rep_init[1], ri2 = cb->rep_init[2];
     const u64 hist_before_block = blk.out_off + B.dict_size;
+    const u32 lstage = smem + KZG_EX_TILE;
+    const u32 mstage = smem + KZG_EX_TILE + KZG_EX_LIT_BYTES + lane * KZG_EX_MSTAGE;
     Win w;
-    w.tile = tile; w.out = out;
+    w.tile = smem; w.out = out;
     w.T0 = -(i32)((uintptr_t)out & 15);
     w.Tv = 0; w.F = 0;
     w.boff = (i64)blk.out_off;
@@ -218,6 +215,14 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     u64 carry = 0;                       // last record of the previous batch
     u64 rec_next = lane < nseq ? seqs[lane] : 0ull;
     i32 cur = 0;
+    // literal staging of the first batch
+    bool lit_staged = false;
+    if (!lfill) {
+        const u32 nv = min(32u, nseq);
+        const u32 l1 = (u32)(__shfl_sync(0xFFFFFFFFu, rec_next, nv - 1) >> 28) & 0x3FFFFu;
+        lit_staged = stage_literals(lstage, lit, 0u, l1, lane);
+    }
+    cp_commit();
 
     for (u32 b0 = 0; b0 < nseq; b0 += 32) {
         const u32 i = b0 + lane;
@@ -227,6 +232,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         u64 prev = __shfl_up_sync(0xFFFFFFFFu, rec, 1);
         if (lane == 0) prev = carry;
         const u32 nvalid = min(32u, nseq - b0);
+        const u32 this_l0 = (u32)(carry >> 28) & 0x3FFFFu;        // literal position the staging area starts at
         carry = __shfl_sync(0xFFFFFFFFu, rec, nvalid - 1);
         const u32 lit_end = (u32)(rec >> 28) & 0x3FFFFu, p_lit_end = (u32)(prev >> 28) & 0x3FFFFu;
         const u32 out_end = (u32)(rec >> 46), p_out_end = (u32)(prev >> 46);
@@ -242,27 +248,67 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         const bool bad = valid && (off == 0 || off >= KZG_OFF_INVALID || (u64)off > hist_before_block + mdst ||
                                    lit_end < p_lit_end || out_end < mdst);
         if (__any_sync(0xFFFFFFFFu, bad)) { err = true; break; }
-        const u32 longm = __ballot_sync(0xFFFFFFFFu, valid && (ll > KZG_EX_LONG || ml > KZG_EX_LONG));
+        const bool islong = valid && (ll > KZG_EX_LONG || ml > KZG_EX_LONG);
+        const u32 longm = __ballot_sync(0xFFFFFFFFu, islong);
         const u32 validm = nvalid == 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        const i32 spos = (i32)mdst - (i32)off;
+        // make room for the whole batch first if it fits a window (the usual case), so that the source
+        // classification below sees the window it will run with
+        {
+            const i32 be = (i32)((u32)(carry >> 46));
+            if (longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
+        }
+
+        // ---- matches whose source left the window long ago: stage the 16-byte chunks covering it now.
+        // (Tv only grows, so "below Tv at batch start" stays true; those bytes were flushed before.)
+        const bool gsrc = valid && !islong && ml > 0 && spos + (i32)ml <= w.Tv && w.boff + spos >= 0;
+        u32 gsa = 0;
+        if (gsrc) {
+            const u8* g = out + spos;
+            const u32 a = (u32)((uintptr_t)g & 15);
+            const u32 nch = (a + ml + 15u) >> 4;             // <= 5
+            g -= a;
+#pragma unroll
+            for (u32 c = 0; c < 5; c++)
+                if (c < nch) cp_async16(mstage + (c << 4), g + (c << 4));
+            gsa = mstage + a;
+        }
+        cp_commit();
+        // literal bytes of this batch were staged one batch ago: all groups but the newest are complete
+        cp_wait<1>();
+        __syncwarp();
+        const bool this_staged = lit_staged;
+        const u32 lsrc_base = lstage + (u32)((uintptr_t)(lit + this_l0) & 15) - this_l0;   // + literal position
+        bool first_round = true;
 
         u32 todo = validm;                               // lanes not yet executed, processed in order
         while (todo) {
-            // next group: the run of lanes before the first long one
-            const u32 first = __ffs(todo) - 1;
+            // next group: lanes up to the next long sequence whose output still fits the window
+            const u32 firstl = __ffs(todo) - 1;
+            const i32 gs = (i32)__shfl_sync(0xFFFFFFFFu, p_out_end, firstl);
             const u32 longs = longm & todo;
             const u32 stop = longs ? (u32)__ffs(longs) - 1 : 32u;      // lane index of the next long sequence
-            const u32 grp = stop >= 32 ? todo : (todo & ((1u << stop) - 1u));
+            const u32 fitm = __ballot_sync(0xFFFFFFFFu, (u32)((i32)out_end - gs) <= KZG_EX_CAP);
+            u32 grp = stop >= 32 ? todo : (todo & ((1u << stop) - 1u));
+            {   // keep the leading run of lanes that fit
+                const u32 nofit = grp & ~fitm;
+                if (nofit) grp &= (1u << (__ffs(nofit) - 1)) - 1u;
+            }
             if (grp) {
                 const u32 lastl = 31 - __clz(grp);
                 const i32 ge = (i32)__shfl_sync(0xFFFFFFFFu, out_end, lastl);
                 if ((u32)(ge - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
                 const bool mine = (grp >> lane) & 1u;
-                // literal runs of the group (no dependencies)
-                lane_copy(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lkind, 0u, lit + p_lit_end, rle);
+                // ---- literal runs of the group (no dependencies)
+                if (this_staged || lfill) {
+                    lane_copy(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lsrc_base + p_lit_end, lfill, rle);
+                } else if (mine) {       // literal range too large to stage (rare): straight from global memory
+                    const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
+                    for (u32 k = 0; k < ll; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
+                }
                 __syncwarp();
-                // matches, in dependency rounds
+                // ---- matches, in dependency rounds
                 bool pending = mine && ml > 0;
-                const i32 spos = (i32)mdst - (i32)off;
                 // source bytes this match needs to be final: everything below `need`
                 const i32 need = off >= ml ? spos + (i32)ml : (i32)mdst;
                 for (;;) {
@@ -270,21 +316,16 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                     if (!pm) break;
                     const i32 fin = (i32)__shfl_sync(0xFFFFFFFFu, mdst, __ffs(pm) - 1);   // all below is final
                     const bool go = pending && need <= fin;
-                    // classify the source
-                    u32 kind = SRC_TILE, n = 0, sa = 0;
-                    const u8* gp = nullptr;
+                    if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
+                    u32 n = 0, sa = 0;
                     bool slow = false;
                     if (go) {
                         n = ml;
-                        if (spos >= w.Tv) {
-                            if (off >= 8) sa = w.tile + (u32)(spos - w.T0);
-                            else slow = true;
-                        } else if (spos + (i32)ml <= w.Tv && w.boff + spos >= 0) {
-                            kind = SRC_GLOBAL; gp = w.out + spos;
-                        } else slow = true;
-                        if (slow) n = 0;
+                        if (gsrc) sa = gsa;
+                        else if (spos >= w.Tv && off >= 8) sa = w.tile + (u32)(spos - w.T0);
+                        else { slow = true; n = 0; }
                     }
-                    lane_copy(w.tile + (u32)((i32)mdst - w.T0), n, kind, sa, gp, 0u);
+                    lane_copy(w.tile + (u32)((i32)mdst - w.T0), n, sa, false, 0u);
                     if (__any_sync(0xFFFFFFFFu, slow)) {
                         if (slow) {     // short period, or a source straddling the window / dictionary boundary: bytes in order
                             const u32 d = w.tile + (u32)((i32)mdst - w.T0);
@@ -301,16 +342,15 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 cur = ge;
                 flush(w, cur, false, lane);
                 todo &= ~grp;
-            }
-            if (stop < 32) {
-                // long sequence `stop`: the warp copies it straight to global memory
+            } else {
+                // the next sequence in order is a long one: the warp copies it straight to global memory
                 const u32 l_ll = __shfl_sync(0xFFFFFFFFu, ll, stop), l_ml = __shfl_sync(0xFFFFFFFFu, ml, stop);
                 const u32 l_ple = __shfl_sync(0xFFFFFFFFu, p_lit_end, stop), l_poe = __shfl_sync(0xFFFFFFFFu, p_out_end, stop);
                 const u32 l_off = __shfl_sync(0xFFFFFFFFu, off, stop);
                 flush(w, cur, true, lane);
                 __syncwarp();
                 u8* d = out + l_poe;
-                if (lit_type == 1) warp_set_global(d, rle, l_ll, lane);
+                if (lfill) warp_set_global(d, rle, l_ll, lane);
                 else warp_copy_global<false>(d, lit + l_ple, l_ll, lane);
                 __threadfence_block();
                 __syncwarp();
@@ -334,9 +374,21 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 w.T0 = cur - (i32)((uintptr_t)(out + cur) & 15);
                 todo &= ~(1u << stop);
             }
-            (void)first;
         }
+        // ---- stage the next batch's literals (this batch no longer reads the staging area)
+        cp_wait<0>();
+        __syncwarp();
+        lit_staged = false;
+        if (!lfill && b0 + 32 < nseq) {
+            const u32 nv = min(32u, nseq - b0 - 32);
+            const u32 l0 = (u32)(carry >> 28) & 0x3FFFFu;
+            const u32 l1 = (u32)(__shfl_sync(0xFFFFFFFFu, rec_next, nv - 1) >> 28) & 0x3FFFFu;
+            if (l1 >= l0) lit_staged = stage_literals(lstage, lit, l0, l1, lane);
+        }
+        cp_commit();
     }
+    cp_wait<0>();
+    __syncwarp();
     if (err) return true;
     // tail: what is left in the window, then the literals after the last sequence
     flush(w, cur, true, lane);
@@ -344,7 +396,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     {
         const u32 used = (u32)(carry >> 28) & 0x3FFFFu;
         if (lit_regen > used) {
-            if (lit_type == 1) warp_set_global(out + cur, rle, lit_regen - used, lane);
+            if (lfill) warp_set_global(out + cur, rle, lit_regen - used, lane);
             else warp_copy_global<false>(out + cur, lit + used, lit_regen - used, lane);
         }
     }
@@ -357,7 +409,7 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32) kzg_exec_kernel(KzgBatch B)
     using namespace kzg_ex;
     extern __shared__ uint4 smem4[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 tile = (u32)__cvta_generic_to_shared(smem4) + warp * KZG_EX_TILE;
+    const u32 smem = (u32)__cvta_generic_to_shared(smem4) + warp * KZG_EX_WARP_SMEM;
     if (B.ctr->overflow & 3u) return;
     for (;;) {
         u32 f = 0;
@@ -380,7 +432,7 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32) kzg_exec_kernel(KzgBatch B)
                     const u8* lit = cb->lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
                     if (cb->lit_type == 1) warp_set_global(out, lit[0], blk.regen, lane);
                     else warp_copy_global<false>(out, lit, blk.regen, lane);
-                } else failed = kzg_exec_sequences(B, blk, cb, out, tile, lane);
+                } else failed = kzg_exec_sequences(B, blk, cb, out, smem, lane);
             }
             __threadfence_block();
             __syncwarp();
