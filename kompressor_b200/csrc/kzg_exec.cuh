@@ -59,8 +59,9 @@ __device__ __forceinline__ u32 ldg8_hist(const u8* p) { return (u32)__ldcg(p); }
 
 // One lane copies n (<= KZG_EX_LONG) bytes from shared address `sa` to shared address `d` (fill: the byte
 // `fillv` instead).  Source and destination may be unaligned; a window -> window source must be at least
-// 8 bytes behind its destination.  Every lane of the warp calls this together (n = 0 for idle lanes): the
-// word loop runs the warp's largest trip count, nothing else loops.
+// 8 bytes behind its destination.  Plain per-lane loops: the warp runs the longest lane's trip count.
+// The word loop may read one aligned word past the last source byte (callers keep that inside their
+// shared memory; the value is never used).
 __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 fillv) {
     const u32 h = min(n, (0u - d) & 3u);
 #pragma unroll
@@ -70,17 +71,17 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 f
     const u32 nw = n >> 2, t = n & 3u;
     const u32 r = (sa & 3u) * 8u;
     u32 A = sa & ~3u;
-    u32 lo = fill ? fillv * 0x01010101u : (nw ? lds32(A) : 0u);
-    const u32 maxw = __reduce_max_sync(0xFFFFFFFFu, nw);
-    for (u32 k = 0; k < maxw; k++) {
-        if (k < nw) {
-            // `lo` is the aligned source word holding the first byte still to copy; the next aligned word is
-            // fetched only if bytes of it are needed (r != 0) or another destination word follows
-            u32 hi = lo;
-            if (!fill) { A += 4; hi = (r != 0 || k + 1 < nw) ? lds32(A) : 0u; }
+    const u32 dend = d + (nw << 2);
+    if (fill) {
+        const u32 fw = fillv * 0x01010101u;
+        for (; d != dend; d += 4) sts32(d, fw);
+    } else if (nw) {
+        u32 lo = lds32(A);
+        for (; d != dend; d += 4) {
+            A += 4;
+            const u32 hi = lds32(A);
             sts32(d, __funnelshift_r(lo, hi, r));
             lo = hi;
-            d += 4;
         }
     }
     const u32 ta = sa + (nw << 2);
@@ -147,7 +148,11 @@ __device__ __forceinline__ void flush(Win& w, i32 upto, bool all, u32 lane) {
     if (nvec > 0) {
         uint4* g = reinterpret_cast<uint4*>(w.out + w.F);
         const u32 t = w.tile + (u32)(w.F - w.T0);
-        for (i32 v = (i32)lane; v < nvec; v += 32) g[v] = lds128(t + ((u32)v << 4));
+        if ((i32)lane < nvec) g[lane] = lds128(t + (lane << 4));
+        if (nvec > 32) {
+#pragma unroll 1
+            for (i32 v = (i32)lane + 32; v < nvec; v += 32) g[v] = lds128(t + ((u32)v << 4));
+        }
         w.F += nvec << 4;
     }
     if (all && w.F < upto) {
@@ -185,7 +190,11 @@ __device__ __forceinline__ bool stage_literals(u32 stage, const u8* lit, u32 l0,
     const u32 a = (u32)((uintptr_t)g0 & 15);
     const u32 nch = (a + (l1 - l0) + 15u) >> 4;             // <= 66
     g0 -= a;
-    for (u32 c = lane; c < nch; c += 32) cp_async16(stage + (c << 4), g0 + ((size_t)c << 4));
+    if (lane < nch) cp_async16(stage + (lane << 4), g0 + (lane << 4));
+    if (nch > 32) {
+#pragma unroll 1
+        for (u32 c = lane + 32; c < nch; c += 32) cp_async16(stage + (c << 4), g0 + ((size_t)c << 4));
+    }
     return true;
 }
 
@@ -259,9 +268,9 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
             if (longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
         }
 
-        // ---- matches whose source left the window long ago: stage the 16-byte chunks covering it now.
-        // (Tv only grows, so "below Tv at batch start" stays true; those bytes were flushed before.)
-        const bool gsrc = valid && !islong && ml > 0 && spos + (i32)ml <= w.Tv && w.boff + spos >= 0;
+        // ---- matches whose source is not (entirely) inside the window any more but has been flushed: stage the
+        // 16-byte chunks covering it now.  (Tv and F only grow, so the classification stays true.)
+        const bool gsrc = valid && !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
         u32 gsa = 0;
         if (gsrc) {
             const u8* g = out + spos;
