@@ -16,6 +16,7 @@
 // the reference call ZSTD_decompressStream (kompressor-zstd--nativelib/src/jvmCommonMain/jni/Wrapper.cpp:178).
 #include "kzg_kernels.cuh"
 #include "kzg_stages.cuh"
+#include "kzg_huf.cuh"
 #include "kzg_fse.cuh"
 #include "kzg_exec.cuh"
 
@@ -38,47 +39,7 @@ __global__ void __launch_bounds__(128) kzg_link_kernel(KzgBatch B) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// huffman: one warp decodes 8 blocks at a time = 32 streams, one thread per stream. The four threads
-// of a block build its 2^maxbits-entry table together in shared memory (4 KiB + 512 B scratch per block).
-#define KZG_HUF_WARPS 2
-#define KZG_HUF_TABLE_BYTES ((1u << KZG_HUF_MAXBITS) * 2u)
-#define KZG_HUF_SMEM (KZG_HUF_WARPS * 8 * (KZG_HUF_TABLE_BYTES + sizeof(KzgHufScratch)))
-__global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B) {
-    extern __shared__ uint4 smem4[];
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 hb = lane >> 2, st = lane & 3;
-    u16* tab = reinterpret_cast<u16*>(smem4) + (size_t)(warp * 8 + hb) * (KZG_HUF_TABLE_BYTES / 2);
-    KzgHufScratch* sc = reinterpret_cast<KzgHufScratch*>(reinterpret_cast<u8*>(smem4) + KZG_HUF_WARPS * 8 * KZG_HUF_TABLE_BYTES) + (warp * 8 + hb);
-    if (B.ctr->overflow & 3u) return;
-    const u32 n = B.ctr->n_hblocks;
-    for (;;) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(&B.ctr->ticket_huf, 1u);
-        g = __shfl_sync(0xFFFFFFFFu, g, 0);
-        if (g * 8 >= n) break;
-        const u32 h = g * 8 + hb;
-        bool valid = h < n;
-        KzgCBlock* cb = nullptr;
-        if (valid) {
-            cb = &B.cblocks[B.hlist[h]];
-            valid = cb->status_lit == KZG_OK && cb->huf_owner != KZG_INVALID_OWNER;
-        }
-        u32 maxbits = 0, nsym = 0;
-        if (valid) {
-            const KzgHufDesc* hd = &B.huf[cb->huf_owner];
-            maxbits = hd->maxbits; nsym = hd->nsym;
-            kzg_huf_build_phase1(sc, hd->weight, nsym, st);
-        }
-        __syncwarp();
-        if (valid) kzg_huf_build_phase2(sc, maxbits, st);
-        __syncwarp();
-        if (valid) kzg_huf_build_phase3(tab, sc, nsym, maxbits, st);
-        __syncwarp();
-        if (valid && st < cb->n_streams) kzg_stage_huf_stream(B, cb, st, tab, maxbits);
-        __syncwarp();
-    }
-}
-
+// huffman: see kzg_huf.cuh (one thread per stream, cp.async bitstream ring, 16 symbols per store)
 // ------------------------------------------------------------------------------------------------
 // fse: see kzg_fse.cuh (one thread per block, lane-interleaved tables, cp.async bitstream ring)
 __global__ void __launch_bounds__(128) kzg_offsets_kernel(KzgBatch B) {
