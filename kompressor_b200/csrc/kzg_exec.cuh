@@ -209,9 +209,12 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     const u8* lit = lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
     const bool lfill = lit_type == 1;
     const u32 rle = lfill ? (u32)lit[0] : 0u;
+    const u32 lit_align = (u32)((uintptr_t)lit & 15);
     const u64* seqs = B.seq_pool + cb->seq_out;
     const u32 ri0 = cb->rep_init[0], ri1 = cb->rep_init[1], ri2 = cb->rep_init[2];
-    const u64 hist_before_block = blk.out_off + B.dict_size;
+    // history available before block position 0 (earlier blocks + dictionary), clamped for 32-bit compares
+    const u64 hist64 = blk.out_off + B.dict_size;
+    const u32 hist_before_block = hist64 > 0x40000000ull ? 0x40000000u : (u32)hist64;
     const u32 lstage = smem + KZG_EX_TILE;
     const u32 mstage = smem + KZG_EX_TILE + KZG_EX_LIT_BYTES + lane * KZG_EX_MSTAGE;
     Win w;
@@ -254,32 +257,31 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
             const u32 base = k == 0 ? ri0 : (k == 1 ? ri1 : ri2);
             off = (base >= KZG_OFF_INVALID || base <= dd) ? KZG_OFF_INVALID : base - dd;
         }
-        const bool bad = valid && (off == 0 || off >= KZG_OFF_INVALID || (u64)off > hist_before_block + mdst ||
-                                   lit_end < p_lit_end || out_end < mdst);
-        if (__any_sync(0xFFFFFFFFu, bad)) { err = true; break; }
-        const bool islong = valid && (ll > KZG_EX_LONG || ml > KZG_EX_LONG);
+        // (the sequence kernel guarantees non-decreasing lit_end / out_end within the block limits)
+        const bool bad = valid && (off - 1u >= KZG_OFF_INVALID - 1u || off > hist_before_block + mdst);
+        const bool islong = ll > KZG_EX_LONG || ml > KZG_EX_LONG;
         const u32 longm = __ballot_sync(0xFFFFFFFFu, islong);
-        const u32 validm = nvalid == 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        if (__any_sync(0xFFFFFFFFu, bad)) { err = true; break; }
         const i32 spos = (i32)mdst - (i32)off;
+        const i32 be = (i32)((u32)(carry >> 46));
         // make room for the whole batch first if it fits a window (the usual case), so that the source
         // classification below sees the window it will run with
-        {
-            const i32 be = (i32)((u32)(carry >> 46));
-            if (longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
-        }
+        if (longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
 
         // ---- matches whose source is not (entirely) inside the window any more but has been flushed: stage the
         // 16-byte chunks covering it now.  (Tv and F only grow, so the classification stays true.)
-        const bool gsrc = valid && !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
+        const bool gsrc = !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
         u32 gsa = 0;
         if (gsrc) {
             const u8* g = out + spos;
             const u32 a = (u32)((uintptr_t)g & 15);
             const u32 nch = (a + ml + 15u) >> 4;             // <= 5
             g -= a;
-#pragma unroll
-            for (u32 c = 0; c < 5; c++)
-                if (c < nch) cp_async16(mstage + (c << 4), g + (c << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(mstage), "l"(g) : "memory");
+            if (nch > 1) asm volatile("cp.async.cg.shared.global [%0+16], [%1+16], 16;" :: "r"(mstage), "l"(g) : "memory");
+            if (nch > 2) asm volatile("cp.async.cg.shared.global [%0+32], [%1+32], 16;" :: "r"(mstage), "l"(g) : "memory");
+            if (nch > 3) asm volatile("cp.async.cg.shared.global [%0+48], [%1+48], 16;" :: "r"(mstage), "l"(g) : "memory");
+            if (nch > 4) asm volatile("cp.async.cg.shared.global [%0+64], [%1+64], 16;" :: "r"(mstage), "l"(g) : "memory");
             gsa = mstage + a;
         }
         cp_commit();
@@ -287,101 +289,103 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         cp_wait<1>();
         __syncwarp();
         const bool this_staged = lit_staged;
-        const u32 lsrc_base = lstage + (u32)((uintptr_t)(lit + this_l0) & 15) - this_l0;   // + literal position
+        const u32 lsrc = lstage + ((lit_align + this_l0) & 15u) - this_l0 + p_lit_end;   // this lane's literals
         bool first_round = true;
 
-        u32 todo = validm;                               // lanes not yet executed, processed in order
-        while (todo) {
-            // next group: lanes up to the next long sequence whose output still fits the window
-            const u32 firstl = __ffs(todo) - 1;
-            const i32 gs = (i32)__shfl_sync(0xFFFFFFFFu, p_out_end, firstl);
-            const u32 longs = longm & todo;
-            const u32 stop = longs ? (u32)__ffs(longs) - 1 : 32u;      // lane index of the next long sequence
-            const u32 fitm = __ballot_sync(0xFFFFFFFFu, (u32)((i32)out_end - gs) <= KZG_EX_CAP);
-            u32 grp = stop >= 32 ? todo : (todo & ((1u << stop) - 1u));
-            {   // keep the leading run of lanes that fit
-                const u32 nofit = grp & ~fitm;
-                if (nofit) grp &= (1u << (__ffs(nofit) - 1)) - 1u;
+        // One group of lanes (`mine`), whose output ends at block position ge and fits the window.
+        auto run_group = [&](bool mine, i32 ge) {
+            // ---- literal runs of the group (no dependencies)
+            if (this_staged || lfill) {
+                lane_copy(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lsrc, lfill, rle);
+            } else if (mine) {       // literal range too large to stage (rare): straight from global memory
+                const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
+                for (u32 k = 0; k < ll; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
             }
-            if (grp) {
-                const u32 lastl = 31 - __clz(grp);
-                const i32 ge = (i32)__shfl_sync(0xFFFFFFFFu, out_end, lastl);
-                if ((u32)(ge - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
-                const bool mine = (grp >> lane) & 1u;
-                // ---- literal runs of the group (no dependencies)
-                if (this_staged || lfill) {
-                    lane_copy(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lsrc_base + p_lit_end, lfill, rle);
-                } else if (mine) {       // literal range too large to stage (rare): straight from global memory
-                    const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
-                    for (u32 k = 0; k < ll; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
-                }
-                __syncwarp();
-                // ---- matches, in dependency rounds
-                bool pending = mine && ml > 0;
-                // source bytes this match needs to be final: everything below `need`
-                const i32 need = off >= ml ? spos + (i32)ml : (i32)mdst;
-                for (;;) {
-                    const u32 pm = __ballot_sync(0xFFFFFFFFu, pending);
-                    if (!pm) break;
-                    const i32 fin = (i32)__shfl_sync(0xFFFFFFFFu, mdst, __ffs(pm) - 1);   // all below is final
-                    const bool go = pending && need <= fin;
-                    if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
-                    u32 n = 0, sa = 0;
-                    bool slow = false;
-                    if (go) {
-                        n = ml;
-                        if (gsrc) sa = gsa;
-                        else if (spos >= w.Tv && off >= 8) sa = w.tile + (u32)(spos - w.T0);
-                        else { slow = true; n = 0; }
-                    }
-                    lane_copy(w.tile + (u32)((i32)mdst - w.T0), n, sa, false, 0u);
-                    if (__any_sync(0xFFFFFFFFu, slow)) {
-                        if (slow) {     // short period, or a source straddling the window / dictionary boundary: bytes in order
-                            const u32 d = w.tile + (u32)((i32)mdst - w.T0);
-                            for (u32 k = 0; k < ml; k++) {
-                                const i32 p = spos + (i32)k;
-                                const u32 v = p >= w.Tv ? lds8(w.tile + (u32)(p - w.T0)) : hist_byte(w, p);
-                                sts8(d + k, v);
-                            }
+            __syncwarp();
+            // ---- matches, in dependency rounds
+            bool pending = mine && ml > 0;
+            // source bytes this match needs to be final: everything below `need`
+            const i32 need = off >= ml ? spos + (i32)ml : (i32)mdst;
+            const bool slow = !gsrc && !(spos >= w.Tv && off >= 8);
+            const u32 sa = gsrc ? gsa : w.tile + (u32)(spos - w.T0);
+            const u32 da = w.tile + (u32)((i32)mdst - w.T0);
+            for (;;) {
+                const u32 pm = __ballot_sync(0xFFFFFFFFu, pending);
+                if (!pm) break;
+                const i32 fin = (i32)__shfl_sync(0xFFFFFFFFu, mdst, __ffs(pm) - 1);   // all below is final
+                const bool go = pending && need <= fin;
+                if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
+                lane_copy(da, (go && !slow) ? ml : 0u, sa, false, 0u);
+                if (__any_sync(0xFFFFFFFFu, go && slow)) {
+                    if (go && slow) {     // short period, or a source straddling the flushed / window boundary: bytes in order
+                        for (u32 k = 0; k < ml; k++) {
+                            const i32 p = spos + (i32)k;
+                            const u32 v = p >= w.Tv ? lds8(w.tile + (u32)(p - w.T0)) : hist_byte(w, p);
+                            sts8(da + k, v);
                         }
                     }
-                    if (go) pending = false;
-                    __syncwarp();
                 }
-                cur = ge;
-                flush(w, cur, false, lane);
-                todo &= ~grp;
-            } else {
-                // the next sequence in order is a long one: the warp copies it straight to global memory
-                const u32 l_ll = __shfl_sync(0xFFFFFFFFu, ll, stop), l_ml = __shfl_sync(0xFFFFFFFFu, ml, stop);
-                const u32 l_ple = __shfl_sync(0xFFFFFFFFu, p_lit_end, stop), l_poe = __shfl_sync(0xFFFFFFFFu, p_out_end, stop);
-                const u32 l_off = __shfl_sync(0xFFFFFFFFu, off, stop);
-                flush(w, cur, true, lane);
+                pending = pending && !go;
                 __syncwarp();
-                u8* d = out + l_poe;
-                if (lfill) warp_set_global(d, rle, l_ll, lane);
-                else warp_copy_global<false>(d, lit + l_ple, l_ll, lane);
-                __threadfence_block();
-                __syncwarp();
-                d += l_ll;
-                const i32 sp = (i32)(l_poe + l_ll) - (i32)l_off;
-                if (l_off >= l_ml && w.boff + sp >= 0) {
-                    warp_copy_global<true>(d, out + sp, l_ml, lane);      // disjoint source inside the frame
+            }
+            cur = ge;
+            flush(w, cur, false, lane);
+        };
+
+        if (longm == 0 && (u32)(be - cur) <= KZG_EX_CAP) {
+            run_group(valid, be);                       // the usual case: the whole batch at once
+        } else {
+            u32 todo = nvalid == 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);     // lanes not yet executed, in order
+            while (todo) {
+                // next group: lanes up to the next long sequence whose output still fits the window
+                const u32 firstl = __ffs(todo) - 1;
+                const i32 gs = (i32)__shfl_sync(0xFFFFFFFFu, p_out_end, firstl);
+                const u32 longs = longm & todo;
+                const u32 stop = longs ? (u32)__ffs(longs) - 1 : 32u;      // lane index of the next long sequence
+                const u32 fitm = __ballot_sync(0xFFFFFFFFu, (u32)((i32)out_end - gs) <= KZG_EX_CAP);
+                u32 grp = stop >= 32 ? todo : (todo & ((1u << stop) - 1u));
+                {   // keep the leading run of lanes that fit
+                    const u32 nofit = grp & ~fitm;
+                    if (nofit) grp &= (1u << (__ffs(nofit) - 1)) - 1u;
+                }
+                if (grp) {
+                    const u32 lastl = 31 - __clz(grp);
+                    const i32 ge = (i32)__shfl_sync(0xFFFFFFFFu, out_end, lastl);
+                    if ((u32)(ge - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
+                    run_group((grp >> lane) & 1u, ge);
+                    todo &= ~grp;
                 } else {
-                    // overlapping (period l_off) or reaching into the dictionary: every byte equals one of the
-                    // l_off bytes just before the match, all of which are final
-                    for (u32 k = lane; k < l_ml; k += 32) {
-                        const i32 p = sp + (i32)(l_off >= l_ml ? k : k % l_off);
-                        const i64 fi = w.boff + p;
-                        d[k] = fi >= 0 ? (u8)ldg8_hist(out + p) : w.dict_end[fi];
+                    // the next sequence in order is a long one: the warp copies it straight to global memory
+                    const u32 l_ll = __shfl_sync(0xFFFFFFFFu, ll, stop), l_ml = __shfl_sync(0xFFFFFFFFu, ml, stop);
+                    const u32 l_ple = __shfl_sync(0xFFFFFFFFu, p_lit_end, stop), l_poe = __shfl_sync(0xFFFFFFFFu, p_out_end, stop);
+                    const u32 l_off = __shfl_sync(0xFFFFFFFFu, off, stop);
+                    flush(w, cur, true, lane);
+                    __syncwarp();
+                    u8* d = out + l_poe;
+                    if (lfill) warp_set_global(d, rle, l_ll, lane);
+                    else warp_copy_global<false>(d, lit + l_ple, l_ll, lane);
+                    __threadfence_block();
+                    __syncwarp();
+                    d += l_ll;
+                    const i32 sp = (i32)(l_poe + l_ll) - (i32)l_off;
+                    if (l_off >= l_ml && w.boff + sp >= 0) {
+                        warp_copy_global<true>(d, out + sp, l_ml, lane);      // disjoint source inside the frame
+                    } else {
+                        // overlapping (period l_off) or reaching into the dictionary: every byte equals one of the
+                        // l_off bytes just before the match, all of which are final
+                        for (u32 k = lane; k < l_ml; k += 32) {
+                            const i32 p = sp + (i32)(l_off >= l_ml ? k : k % l_off);
+                            const i64 fi = w.boff + p;
+                            d[k] = fi >= 0 ? (u8)ldg8_hist(out + p) : w.dict_end[fi];
+                        }
                     }
+                    __threadfence_block();
+                    __syncwarp();
+                    cur = (i32)(l_poe + l_ll + l_ml);
+                    w.F = w.Tv = cur;
+                    w.T0 = cur - (i32)((uintptr_t)(out + cur) & 15);
+                    todo &= ~(1u << stop);
                 }
-                __threadfence_block();
-                __syncwarp();
-                cur = (i32)(l_poe + l_ll + l_ml);
-                w.F = w.Tv = cur;
-                w.T0 = cur - (i32)((uintptr_t)(out + cur) & 15);
-                todo &= ~(1u << stop);
             }
         }
         // ---- stage the next batch's literals (this batch no longer reads the staging area)
