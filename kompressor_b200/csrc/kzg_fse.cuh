@@ -75,13 +75,22 @@ __device__ __forceinline__ u32 build_table(u32 tab, u32 ring, const KzgFseDesc* 
             do { pos = (pos + step) & mask; } while (pos >= high);
         }
     }
-    for (u32 i = 0; i < size; i++) {
+    // numbering pass, four cells at a time: the loads of a group are independent, so the shared-memory
+    // latency is paid once per group instead of once per cell; cells of a group that share a symbol are
+    // counted by comparison, and the counters are stored in order so the last duplicate wins
+    for (u32 i = 0; i < size; i += 4) {
         const u32 a = tab + (i << 6);
-        const u32 s = lds16(a);
-        const u32 sa = scr_addr(ring, s);
-        const u32 v = lds16(sa);
-        sts16(sa, v + 1);
-        sts16(a, ((v & 0x7FFFu) << 6) | s);
+        const u32 s0 = lds16(a), s1 = lds16(a + 64), s2 = lds16(a + 128), s3 = lds16(a + 192);
+        const u32 a0 = scr_addr(ring, s0), a1 = scr_addr(ring, s1), a2 = scr_addr(ring, s2), a3 = scr_addr(ring, s3);
+        const u32 v0 = lds16(a0);
+        const u32 v1 = lds16(a1) + (s1 == s0);
+        const u32 v2 = lds16(a2) + (s2 == s0) + (s2 == s1);
+        const u32 v3 = lds16(a3) + (s3 == s0) + (s3 == s1) + (s3 == s2);
+        sts16(a0, v0 + 1); sts16(a1, v1 + 1); sts16(a2, v2 + 1); sts16(a3, v3 + 1);
+        sts16(a, ((v0 & 0x7FFFu) << 6) | s0);
+        sts16(a + 64, ((v1 & 0x7FFFu) << 6) | s1);
+        sts16(a + 128, ((v2 & 0x7FFFu) << 6) | s2);
+        sts16(a + 192, ((v3 & 0x7FFFu) << 6) | s3);
     }
     return log;
 }
@@ -280,13 +289,14 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
                 // up to 3 new chunks (384 bits >= 4 x 89, the most four sequences can consume) are requested.
                 cp_wait<1>();
                 ready_lo = pend2;
+                // request up to 3 chunks, as far down as the ring allows (slot of chunk c + 8 must be dead)
                 const i32 cP = P >> 7;
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-                    if (next_c >= 0 && next_c > cP - KZG_FSE_RING_CHUNKS) {
-                        cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4));
-                        next_c--;
-                    }
+                const i32 want = min(min(next_c - (cP - KZG_FSE_RING_CHUNKS), next_c + 1), 3);
+                const u8* gsrc = base + ((i64)next_c << 4);
+                if (want > 0) cp_async16(s_ring + (((u32)next_c & 7u) << 4), gsrc);
+                if (want > 1) cp_async16(s_ring + (((u32)(next_c - 1) & 7u) << 4), gsrc - 16);
+                if (want > 2) cp_async16(s_ring + (((u32)(next_c - 2) & 7u) << 4), gsrc - 32);
+                next_c -= max(want, 0);
                 cp_commit();
                 pend2 = pend1;
                 pend1 = next_c + 1;
