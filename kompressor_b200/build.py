@@ -39,5 +39,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def find_jni_include() -> list[str]:
+    """Include directories of a JDK's <jni.h>, or [] (this image has no JDK)."""
+    cands = [os.environ.get("JAVA_HOME", "")] + sorted(
+        os.path.join("/usr/lib/jvm", d) for d in (os.listdir("/usr/lib/jvm") if os.path.isdir("/usr/lib/jvm") else []))
+    for c in cands:
+        inc = os.path.join(c, "include")
+        if c and os.path.exists(os.path.join(inc, "jni.h")):
+            return [inc, os.path.join(inc, "linux")]
+    return []
+
+
+def build_jni(force: bool = False) -> str | None:
+    """Layer C: libzstd-jni-kzg.so with the Java_com_ensody_kompressor_zstd_ZstdWrapper_* decompress symbols
+    (csrc/kzg_jni.cpp), linked against libkzg.so.  Returns None where no JDK headers exist."""
+    inc = find_jni_include()
+    if not inc:
+        return None
+    out = os.path.join(HERE, "libzstd-jni-kzg.so")
+    src = os.path.join(CSRC, "kzg_jni.cpp")
+    if force or not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        build()
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src] + [f"-I{i}" for i in inc] + \
+              [f"-L{HERE}", "-lkzg", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))

@@ -82,3 +82,18 @@ def test_product_never_touches_oracle():
                 text = open(os.path.join(base, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text, f
                 assert "hostsim" not in text or f.endswith(".cuh"), f
+
+
+def test_jni_shim_typechecks_and_names_the_reference_symbols():
+    """Layer C (kzg_jni.cpp) cannot be linked without a JDK; check that it compiles against the minimal
+    jni.h stub and defines exactly the decompress-side symbols Kompressor's ZstdWrapper binds
+    (kompressor-zstd--nativelib/src/jvmCommonMain/kotlin/com/ensody/kompressor/zstd/ZstdWrapper.kt:24-60)."""
+    import subprocess
+    src = os.path.join(ROOT, "kompressor_b200", "csrc", "kzg_jni.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "tests", "jni_stub"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    defined = set(re.findall(r"JNICALL\s+(Java_com_ensody_kompressor_zstd_ZstdWrapper_\w+|JNI_On\w+)\s*\(", text))
+    assert defined == {"JNI_OnLoad", "JNI_OnUnload"} | {"Java_com_ensody_kompressor_zstd_ZstdWrapper_" + n for n in (
+        "createDecompressor", "freeDecompressor", "loadDecompressorDictionary", "decompressStream", "getErrorName")}
