@@ -59,24 +59,31 @@ __device__ __forceinline__ u32 ldg8_hist(const u8* p) { return (u32)__ldcg(p); }
 
 // One lane copies n (<= KZG_EX_LONG) bytes from shared address `sa` to shared address `d` (fill: the byte
 // `fillv` instead).  Source and destination may be unaligned; a window -> window source must be at least
-// 8 bytes behind its destination.  Plain per-lane loops: the warp runs the longest lane's trip count.
-// The word loop may read one aligned word past the last source byte (callers keep that inside their
-// shared memory; the value is never used).
+// 8 bytes behind its destination.  The source is read only as aligned words (combined by funnel shifts);
+// the ragged head and tail of the destination are byte stores of an already assembled word, so no store
+// waits on a byte load.  Up to two aligned words past the last source byte may be read (callers keep
+// that inside their shared memory; the values are never used).
 __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 fillv) {
+    if (n == 0) return;
     const u32 h = min(n, (0u - d) & 3u);
-#pragma unroll
-    for (u32 k = 0; k < 3; k++)
-        if (k < h) sts8(d + k, fill ? fillv : lds8(sa + k));
-    d += h; sa += h; n -= h;
-    const u32 nw = n >> 2, t = n & 3u;
-    const u32 r = (sa & 3u) * 8u;
-    u32 A = sa & ~3u;
-    const u32 dend = d + (nw << 2);
+    u32 A = sa & ~3u, w0, w1;
+    if (fill) w0 = w1 = fillv * 0x01010101u;
+    else { w0 = lds32(A); w1 = lds32(A + 4); }
+    {
+        const u32 v = __funnelshift_r(w0, w1, (sa & 3u) << 3);
+        if (h > 0) sts8(d, v);
+        if (h > 1) sts8(d + 1, v >> 8);
+        if (h > 2) sts8(d + 2, v >> 16);
+    }
+    d += h; n -= h;
+    const u32 sb = (sa & 3u) + h;               // source byte offset inside w0:w1 after the head (0..6)
+    const u32 r = (sb & 3u) << 3;
+    u32 lo = sb >= 4u ? w1 : w0;
+    A += sb >= 4u ? 4u : 0u;
+    const u32 dend = d + (n & ~3u);
     if (fill) {
-        const u32 fw = fillv * 0x01010101u;
-        for (; d != dend; d += 4) sts32(d, fw);
-    } else if (nw) {
-        u32 lo = lds32(A);
+        for (; d != dend; d += 4) sts32(d, w0);
+    } else {
         for (; d != dend; d += 4) {
             A += 4;
             const u32 hi = lds32(A);
@@ -84,10 +91,14 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 f
             lo = hi;
         }
     }
-    const u32 ta = sa + (nw << 2);
-#pragma unroll
-    for (u32 k = 0; k < 3; k++)
-        if (k < t) sts8(d + k, fill ? fillv : lds8(ta + k));
+    const u32 t = n & 3u;
+    if (t) {
+        const u32 hi = fill ? w0 : lds32(A + 4);
+        const u32 v = __funnelshift_r(lo, hi, r);
+        sts8(d, v);
+        if (t > 1) sts8(d + 1, v >> 8);
+        if (t > 2) sts8(d + 2, v >> 16);
+    }
 }
 
 // Warp-cooperative global -> global copy of disjoint ranges, 16-byte vector stores.
@@ -226,6 +237,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     bool err = false;
     u64 carry = 0;                       // last record of the previous batch
     u64 rec_next = lane < nseq ? seqs[lane] : 0ull;
+    const u64* rec_ptr = seqs + lane;
     i32 cur = 0;
     // literal staging of the first batch
     bool lit_staged = false;
@@ -240,7 +252,8 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         const u32 i = b0 + lane;
         const bool valid = i < nseq;
         const u64 rec = rec_next;
-        rec_next = (i + 32 < nseq) ? seqs[i + 32] : 0ull;          // prefetch the next batch
+        rec_ptr += 32;
+        rec_next = (i + 32 < nseq) ? *rec_ptr : 0ull;              // prefetch the next batch
         u64 prev = __shfl_up_sync(0xFFFFFFFFu, rec, 1);
         if (lane == 0) prev = carry;
         const u32 nvalid = min(32u, nseq - b0);
@@ -307,6 +320,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
             // source bytes this match needs to be final: everything below `need`
             const i32 need = off >= ml ? spos + (i32)ml : (i32)mdst;
             const bool slow = !gsrc && !(spos >= w.Tv && off >= 8);
+            const bool anyslow = __any_sync(0xFFFFFFFFu, pending && slow);
             const u32 sa = gsrc ? gsa : w.tile + (u32)(spos - w.T0);
             const u32 da = w.tile + (u32)((i32)mdst - w.T0);
             for (;;) {
@@ -316,7 +330,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 const bool go = pending && need <= fin;
                 if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
                 lane_copy(da, (go && !slow) ? ml : 0u, sa, false, 0u);
-                if (__any_sync(0xFFFFFFFFu, go && slow)) {
+                if (anyslow) {
                     if (go && slow) {     // short period, or a source straddling the flushed / window boundary: bytes in order
                         for (u32 k = 0; k < ml; k++) {
                             const i32 p = spos + (i32)k;
@@ -418,7 +432,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     return false;
 }
 
-__global__ void __launch_bounds__(KZG_EX_WARPS * 32) kzg_exec_kernel(KzgBatch B) {
+__global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch B) {
     using namespace kzg_ex;
     extern __shared__ uint4 smem4[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

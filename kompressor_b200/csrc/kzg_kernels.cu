@@ -89,11 +89,24 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
         const u64 stripes = len >> 5;
         const u8* s = p + 8 * q;
         u64 k = 0;
-        for (; k + 4 <= stripes; k += 4) {
-            const u64 x0 = kzg_ld64_any(s + 32 * k), x1 = kzg_ld64_any(s + 32 * (k + 1)),
-                      x2 = kzg_ld64_any(s + 32 * (k + 2)), x3 = kzg_ld64_any(s + 32 * (k + 3));
-            acc = kzg_xxround(acc, x0); acc = kzg_xxround(acc, x1);
-            acc = kzg_xxround(acc, x2); acc = kzg_xxround(acc, x3);
+        // 16 independent loads in flight per lane: the rounds themselves are a serial chain, the loads are not
+        if (((uintptr_t)s & 7) == 0) {
+            const u64* s64 = reinterpret_cast<const u64*>(s);
+            for (; k + 16 <= stripes; k += 16) {
+                u64 x[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) x[j] = __ldcs(s64 + 4 * (k + j));
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc = kzg_xxround(acc, x[j]);
+            }
+        } else {
+            for (; k + 8 <= stripes; k += 8) {
+                u64 x[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) x[j] = kzg_ld64_any(s + 32 * (k + j));
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc = kzg_xxround(acc, x[j]);
+            }
         }
         for (; k < stripes; k++) acc = kzg_xxround(acc, kzg_ld64_any(s + 32 * k));
     }
