@@ -2,34 +2,49 @@
 // one GPU thread per compressed block, 32 blocks per warp.  Device-only code.
 //
 // The state machine is a serial dependency chain per block (state -> table cell -> bit count -> bits
-// -> next state), so the kernel is latency-bound and the design goal is the shortest chain with the
-// fewest instructions, with no divergence inside a warp:
+// -> next state).  A single warp can only issue that chain one dependent instruction after another, so
+// the kernel is bound by instructions per sequence, not by bandwidth.  The design therefore minimises
+// and splits the per-sequence instruction stream:
+//   * warp specialisation: every group of 32 blocks is served by a PAIR of warps on two different
+//     schedulers.  The "chain" warp does only what the next state depends on (table lookups, bit
+//     counts, state update, bit position); the "post" warp turns the raw fields into values, keeps the
+//     repeat-offset history, accumulates lit_end / out_end, packs and stores the 8-byte records.  The
+//     two meet through a double-buffered shared-memory queue (4 sequences per hand-over) guarded by
+//     named barriers (bar.arrive / bar.sync), never by spinning;
 //   * tables live in shared memory, interleaved by lane: cell i of lane L is the u16 at byte
-//     (i << 6) + (L << 1) of the warp's table area, so a lookup costs one shift-add and lanes collide at
-//     most pairwise (two lanes share a 32-bit bank column);
+//     (i << 6) + (L << 1) of the pair's table area, so a lookup costs one multiply-add and lanes collide
+//     at most pairwise (two lanes share a 32-bit bank column); the chain warp builds the LL and OF tables
+//     while the post warp builds ML;
 //   * the backward bitstream is staged by cp.async (LDGSTS, no destination register, so no per-warp
 //     scoreboard stall) into a per-lane ring of eight 16-byte chunks (128 contiguous bytes per lane);
 //     copies are issued only at warp-uniform points (every 4 sequences), sized so that the ring always
 //     covers the most bits four sequences can consume (4 x 89);
 //   * every sequence re-reads a 64-bit window at its current bit position from that ring (3 LDS + 2
-//     funnel shifts, off the critical chain) and extracts all six bit fields with clamped funnel
-//     shifts: no refill branches, no window register rotation;
-//   * repeat-offset history is kept in registers and updated with selects.
+//     funnel shifts, off the critical chain) and all six bit fields come out of it with clamped funnel
+//     shifts: no refill branches, no window register rotation; the loop body is straight-line code and
+//     lanes that ran out of sequences keep computing on frozen positions;
+//   * sequences carrying more than 32 extra bits at once (possible only with huge offsets and lengths)
+//     make the lane fall back to a general decoder for that block after the loop.
 // What libzstd does here is ZSTD_decodeSequence / ZSTD_buildFSETable, reached from the reference through
 // ZSTD_decompressStream (kompressor-zstd--nativelib/src/jvmCommonMain/jni/Wrapper.cpp:178).
 #pragma once
 #include "kzg_stages.cuh"
 
-#define KZG_FSE_WARPS 2
+#define KZG_FSE_PAIRS 2                                     // warp pairs per CTA (one CTA per SM)
+#define KZG_FSE_WARPS (2 * KZG_FSE_PAIRS)
 #define KZG_FSE_CELLS 1280                                  // LL 512 | ML 512 | OF 256
-#define KZG_FSE_TAB_BYTES (KZG_FSE_CELLS * 64)              // per warp: 32 lanes x 1280 cells x 2 B
+#define KZG_FSE_TAB_BYTES (KZG_FSE_CELLS * 64)              // per pair: 32 lanes x 1280 cells x 2 B
 #define KZG_FSE_RING_CHUNKS 8
-#define KZG_FSE_RING_BYTES (KZG_FSE_RING_CHUNKS * 512)      // per warp: 32 lanes x (8 chunks x 16 B, contiguous per lane)
+#define KZG_FSE_RING_BYTES (KZG_FSE_RING_CHUNKS * 512)      // per pair: 32 lanes x (8 chunks x 16 B, contiguous per lane)
+#define KZG_FSE_SCR_BYTES 4096                              // per pair: table-build scratch of the post warp
+#define KZG_FSE_SERVICE 4                                   // sequences per hand-over / between ring service points
+#define KZG_FSE_Q_BYTES (2 * KZG_FSE_SERVICE * 1024)        // per pair: 2 buffers x 4 sequences x 32 lanes x 32 B
+#define KZG_FSE_MISC_BYTES 512                              // per pair: ticket, trip count, per-lane hand-over words
+#define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_SCR_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
 #define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
-#define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_WARPS * (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES))
-#define KZG_FSE_SERVICE 4                                   // sequences between ring service points
+#define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
 #ifndef KZG_FSE_WIDE_LIMIT
-#define KZG_FSE_WIDE_LIMIT 32u                               // most extra bits per sequence the fast loop extracts (tests lower it)
+#define KZG_FSE_WIDE_LIMIT 32u                              // most extra bits per sequence the fast loop extracts (tests lower it)
 #endif
 
 namespace kzg_fse {
@@ -38,6 +53,16 @@ __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_gen
 __device__ __forceinline__ u32 lds16(u32 a) { u16 v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((u16)v)); }
 __device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(u32 a, u32 x, u32 y, u32 z, u32 w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void lds128(u32 a, u32& x, u32& y, u32& z, u32& w) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a) : "memory");
+}
+// Named barriers over the 64 threads of a warp pair: sync waits, arrive only signals.
+__device__ __forceinline__ void bar_sync(u32 id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive(u32 id) { asm volatile("bar.arrive %0, 64;" :: "r"(id) : "memory"); }
 __device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
@@ -176,25 +201,35 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
 
 }  // namespace kzg_fse
 
+// Queue entry of one sequence of one lane (32 bytes): {hi, lo, pLL, pML} + {ofc}.
+//   hi:lo  64-bit window at the sequence's bit position        pLL / pML  packed code entries (bits << 24 | base)
 __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch B) {
     using namespace kzg_fse;
     extern __shared__ uint4 smem4[];
     u32* llx = reinterpret_cast<u32*>(smem4);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 pair = warp >> 1;
+    const bool chain = (warp & 1u) == 0;                   // even warp: chain, odd warp: post
     for (u32 k = threadIdx.x; k < KZG_FSE_CODE_WORDS; k += blockDim.x) llx[k] = k < 89 ? B.code_tables[k] : 0u;
     __syncthreads();
     const u32 s_llx = smem_addr(llx), s_mlx = s_llx + 36 * 4;
-    const u32 s_warp = s_llx + KZG_FSE_CODE_WORDS * 4 + warp * (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES);
-    const u32 s_tab = s_warp + (lane << 1);
-    const u32 s_ring = s_warp + KZG_FSE_TAB_BYTES + (lane << 7);
+    const u32 s_pair = s_llx + KZG_FSE_CODE_WORDS * 4 + pair * KZG_FSE_PAIR_SMEM;
+    const u32 s_tab = s_pair + (lane << 1);
+    const u32 s_ring = s_pair + KZG_FSE_TAB_BYTES + (lane << 7);
+    const u32 s_scr = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + (lane << 7);
+    const u32 s_q = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_SCR_BYTES + (lane << 5);
+    const u32 s_misc = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_SCR_BYTES + KZG_FSE_Q_BYTES;
+    const u32 s_lane = s_misc + 64 + (lane << 2);           // per-lane hand-over word
     const u32 tLL = s_tab, tML = s_tab + (512u << 6), tOF = s_tab + (1024u << 6);
+    // barrier ids of this pair (0 is __syncthreads)
+    const u32 BAR_PAIR = 1 + pair * 5, BAR_FULL = 2 + pair * 5, BAR_EMPTY = 4 + pair * 5;
     if (B.ctr->overflow & 3u) return;
     const u32 n = B.ctr->n_sblocks;
 
     for (;;) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(&B.ctr->ticket_fse, 1u);
-        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        if (chain && lane == 0) sts32(s_misc, atomicAdd(&B.ctr->ticket_fse, 1u));
+        bar_sync(BAR_PAIR);
+        const u32 g = lds32(s_misc);
         if (g * 32 >= n) break;
         const u32 si = g * 32 + lane;
         KzgCBlock* cb = nullptr;
@@ -206,44 +241,54 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
             cb = &B.cblocks[B.slist[si]];
             if (cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) j.nseq = cb->n_seq;
         }
-        // ---- tables (per lane, in its own column; the ring doubles as build scratch).  Idle lanes get
-        // one-cell tables so that the branch-free loop below stays in bounds for them too.
+        // ---- tables, in the lane's column: the chain warp builds LL and OF (scratch = its idle ring), the
+        // post warp builds ML.  Idle lanes get one-cell tables so the straight-line loop stays in bounds.
         if (j.nseq) {
             const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-            j.logLL = build_table(tLL, s_ring, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
-            j.logOF = build_table(tOF, s_ring, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
-            j.logML = build_table(tML, s_ring, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
-        } else { sts16(tLL, 1u << 6); sts16(tOF, 1u << 6); sts16(tML, 1u << 6); }
-        __syncwarp();
-        // ---- bitstream set-up
+            if (chain) {
+                j.logLL = build_table(tLL, s_ring, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
+                j.logOF = build_table(tOF, s_ring, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
+                const KzgFseDesc* d2 = o2 == KZG_NONE ? B.fse_default : &B.fse[o2];
+                j.logML = d2->kind[2] == 1 ? 0u : (u32)d2->log[2];
+            } else {
+                j.logML = build_table(tML, s_scr, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
+            }
+            j.lit_regen = cb->lit_regen;
+            j.block_max = B.frames[cb->frame].block_max;
+            j.out = B.seq_pool + cb->seq_out;
+            if (!cb->first_in_frame) { j.rep0 = KZG_OFF_SYM | 0; j.rep1 = KZG_OFF_SYM | 1; j.rep2 = KZG_OFF_SYM | 2; }
+        } else if (chain) { sts16(tLL, 1u << 6); sts16(tOF, 1u << 6); sts16(tML, 1u << 6); }
         Result res;
         res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;
-        if (j.nseq && !cb->first_in_frame) { j.rep0 = KZG_OFF_SYM | 0; j.rep1 = KZG_OFF_SYM | 1; j.rep2 = KZG_OFF_SYM | 2; }
         res.rep0 = j.rep0; res.rep1 = j.rep1; res.rep2 = j.rep2;
+
+        // ---- bitstream set-up (chain warp); the effective sequence count goes to the post warp
         const u8* base = nullptr;
-        i32 next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
-        if (j.nseq) {
-            const u8* start = B.src + cb->src + cb->seq_src;
-            const u32 size = cb->seq_size;
-            const u32 last = size ? start[size - 1] : 0u;
-            if (last == 0) j.nseq = 0;                     // no padding marker: corrupt (status stays CORRUPTION)
-            else {
-                base = (const u8*)((uintptr_t)start & ~(uintptr_t)15);
-                j.base32 = reinterpret_cast<const u32*>(base);
-                j.lowbits = (i32)(8u * (u32)(start - base));
-                j.P0 = j.lowbits + (i32)(8u * (size - 1)) + kzg_highbit(last);
-                j.out = B.seq_pool + cb->seq_out;
-                j.lit_regen = cb->lit_regen;
-                j.block_max = B.frames[cb->frame].block_max;
-                next_c = j.P0 >> 7;
-                for (int r = 0; r < KZG_FSE_RING_CHUNKS; r++)
-                    if (next_c >= 0) { cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4)); next_c--; }
+        i32 next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0, P = 0;
+        u32 sLL = 0, sOF = 0, sML = 0;
+        u32 nseq = j.nseq;
+        bar_sync(BAR_PAIR);                                  // tables complete (all three, both warps)
+        if (chain) {
+            if (nseq) {
+                const u8* start = B.src + cb->src + cb->seq_src;
+                const u32 size = cb->seq_size;
+                const u32 last = size ? start[size - 1] : 0u;
+                if (last == 0) nseq = 0;                   // no padding marker: corrupt (status stays CORRUPTION)
+                else {
+                    base = (const u8*)((uintptr_t)start & ~(uintptr_t)15);
+                    j.base32 = reinterpret_cast<const u32*>(base);
+                    j.lowbits = (i32)(8u * (u32)(start - base));
+                    j.P0 = j.lowbits + (i32)(8u * (size - 1)) + kzg_highbit(last);
+                    next_c = j.P0 >> 7;
+                    for (int r = 0; r < KZG_FSE_RING_CHUNKS; r++)
+                        if (next_c >= 0) { cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4)); next_c--; }
+                }
             }
+            cp_commit();
+            cp_wait<0>();
+            ready_lo = pend1 = pend2 = next_c + 1;
+            P = j.P0;
         }
-        cp_commit();
-        cp_wait<0>();
-        ready_lo = pend1 = pend2 = next_c + 1;
-        i32 P = j.P0;
 
         // 64-bit window [P-64, P) -> hi:lo from the lane's ring (word w of the stream sits at (w & 31) * 4)
 #define KZG_FSE_WINDOW(hi, lo)                                                     \
@@ -256,113 +301,161 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
             lo = __funnelshift_r(w0_, w1_, q_);                                    \
         }
 
-        // ---- initial states: LL, OF, ML (Appendix A.6)
-        u32 sLL = 0, sOF = 0, sML = 0;
-        u32 nseq = j.nseq;
-        if (nseq) {
-            u32 hi, lo;
-            KZG_FSE_WINDOW(hi, lo);
-            if (lo == 0xFFFFFFFFu && hi == 0u) hi = 0u;    // (lo is unused here)
-            sLL = __funnelshift_lc(hi, 0u, j.logLL);
-            const u32 x1 = hi << j.logLL;
-            sOF = __funnelshift_lc(x1, 0u, j.logOF);
-            const u32 x2 = x1 << j.logOF;
-            sML = __funnelshift_lc(x2, 0u, j.logML);
-            P -= (i32)(j.logLL + j.logOF + j.logML);
-            if (P < j.lowbits) nseq = 0;
-        }
-        const u32 szLL = 1u << j.logLL, szOF = 1u << j.logOF, szML = 1u << j.logML;
-        const u32 kLL = j.logLL - 31u, kOF = j.logOF - 31u, kML = j.logML - 31u;   // nbBits = k + clz(next)
-        u32 rep0 = j.rep0, rep1 = j.rep1, rep2 = j.rep2;
-        u32 lit_end = 0, out_end = 0, ovf = 0;
-        bool wide = false;                       // a sequence with more than 32 extra bits was seen
-        u64* out = j.out;
-        u32 nmax = nseq;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
-
-        // The loop body is straight-line code: lanes that ran out of sequences keep computing on frozen
-        // positions (their stores, bit consumption and history updates are masked off).
-        for (u32 i0 = 0; i0 < nmax; i0 += KZG_FSE_SERVICE) {
-            {
-                // ring service (warp-uniform point). Chunks issued two service points ago are complete now;
-                // up to 3 new chunks (384 bits >= 4 x 89, the most four sequences can consume) are requested.
-                cp_wait<1>();
-                ready_lo = pend2;
-                // request up to 3 chunks, as far down as the ring allows (slot of chunk c + 8 must be dead)
-                const i32 cP = P >> 7;
-                const i32 want = min(min(next_c - (cP - KZG_FSE_RING_CHUNKS), next_c + 1), 3);
-                const u8* gsrc = base + ((i64)next_c << 4);
-                if (want > 0) cp_async16(s_ring + (((u32)next_c & 7u) << 4), gsrc);
-                if (want > 1) cp_async16(s_ring + (((u32)(next_c - 1) & 7u) << 4), gsrc - 16);
-                if (want > 2) cp_async16(s_ring + (((u32)(next_c - 2) & 7u) << 4), gsrc - 32);
-                next_c -= max(want, 0);
-                cp_commit();
-                pend2 = pend1;
-                pend1 = next_c + 1;
-                // lowest chunk the next four sequences can touch: 4 x 89 bits + 64-bit window + 31
-                const i32 need_lo = max((P - 451) >> 7, 0);
-                if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }     // rare: wait for everything
-            }
-#pragma unroll
-            for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
-                const u32 i = i0 + u;
-                const bool act = i < nseq, notlast = i + 1 < nseq;
-                const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
+        if (chain) {
+            // initial states: LL, OF, ML (Appendix A.6)
+            if (nseq) {
                 u32 hi, lo;
                 KZG_FSE_WINDOW(hi, lo);
-                const u32 ofc = eOF & 63u;
-                const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
-                const u32 llb = pLL >> 24, mlb = pML >> 24;
-                const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
-                // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
-                const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
-                const u32 E = ofc + mlb + llb;
-                wide |= act && E > KZG_FSE_WIDE_LIMIT;
-                // all six fields straight out of the 64-bit window (valid when E <= 32: E + 26 <= 58 bits)
-                const u32 ofx = __funnelshift_lc(hi, 0u, ofc);
-                const u32 mlx_ = __funnelshift_lc(__funnelshift_l(lo, hi, ofc), 0u, mlb);
-                const u32 llx_ = __funnelshift_lc(__funnelshift_lc(lo, hi, ofc + mlb), 0u, llb);
-                const u32 X = __funnelshift_lc(lo, hi, E);
-                const u32 X2 = X << bLL, X3 = X2 << bML;
-                sLL = (nLL << bLL) - szLL + __funnelshift_lc(X, 0u, bLL);
-                sML = (nML << bML) - szML + __funnelshift_lc(X2, 0u, bML);
-                sOF = (nOF << bOF) - szOF + __funnelshift_lc(X3, 0u, bOF);
-                P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
-                const u32 ofv = (1u << ofc) + ofx;
-                const u32 ml = act ? (pML & 0xFFFFFFu) + mlx_ : 0u;
-                const u32 ll = act ? (pLL & 0xFFFFFFu) + llx_ : 0u;
-                // repeat-offset history (Appendix A.6) with selects.  "rep0 - 1": a symbolic value counts its
-                // decrement in bits [2,27) (+4), a concrete one just loses 1 (0 is rejected at execution).
-                const bool isrep = ofc < 2u;                         // ofv in {1, 2, 3}
-                const u32 idx = ofv - 1u + (ll == 0u ? 1u : 0u);     // meaningful when isrep
-                const u32 dec = rep0 - 1u + (rep0 >> 27) * 5u;
-                u32 cand = idx == 1u ? rep1 : rep0;
-                cand = idx == 2u ? rep2 : cand;
-                cand = idx == 3u ? dec : cand;
-                const u32 off = isrep ? cand : min(ofv - 3u, (u32)KZG_OFF_INVALID);
-                rep2 = ((isrep && idx <= 1u) || !act) ? rep2 : rep1;
-                rep1 = ((isrep && idx == 0u) || !act) ? rep1 : rep0;
-                rep0 = act ? off : rep0;
-                lit_end += ll;
-                out_end += ll + ml;
-                ovf |= out_end;           // one sequence adds < 2^18, so any overflow past 2^18 leaves a high bit here
-                if (act) out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
+                if (lo == 0xFFFFFFFFu && hi == 0u) hi = 0u;    // (lo is unused here)
+                sLL = __funnelshift_lc(hi, 0u, j.logLL);
+                const u32 x1 = hi << j.logLL;
+                sOF = __funnelshift_lc(x1, 0u, j.logOF);
+                const u32 x2 = x1 << j.logOF;
+                sML = __funnelshift_lc(x2, 0u, j.logML);
+                P -= (i32)(j.logLL + j.logOF + j.logML);
+                if (P < j.lowbits) nseq = 0;
+            }
+            sts32(s_lane, nseq);
+            u32 nmax = nseq;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
+            if (lane == 0) sts32(s_misc + 4, nmax);
+        }
+        bar_sync(BAR_PAIR);
+        const u32 nmax = lds32(s_misc + 4);
+        nseq = lds32(s_lane);
+        const u32 nint = (nmax + KZG_FSE_SERVICE - 1) / KZG_FSE_SERVICE;     // hand-overs in this round
+
+        if (chain) {
+            // =================================================================== chain warp
+            const u32 szLL = 1u << j.logLL, szOF = 1u << j.logOF, szML = 1u << j.logML;
+            const u32 kLL = j.logLL - 31u, kOF = j.logOF - 31u, kML = j.logML - 31u;   // nbBits = k + clz(next)
+            bool wide = false;                   // a sequence with more than 32 extra bits was seen
+            for (u32 t = 0; t < nint; t++) {
+                const u32 buf = t & 1u;
+                if (t >= 2) bar_sync(BAR_EMPTY + buf);            // the post warp is done with this buffer
+                {
+                    // ring service (warp-uniform point). Chunks issued two service points ago are complete now;
+                    // up to 3 new chunks (384 bits >= 4 x 89, the most four sequences can consume) are requested,
+                    // as far down as the ring allows (the slot of chunk c + 8 must be dead).
+                    cp_wait<1>();
+                    ready_lo = pend2;
+                    const i32 cP = P >> 7;
+                    const i32 want = min(min(next_c - (cP - KZG_FSE_RING_CHUNKS), next_c + 1), 3);
+                    const u8* gsrc = base + ((i64)next_c << 4);
+                    if (want > 0) cp_async16(s_ring + (((u32)next_c & 7u) << 4), gsrc);
+                    if (want > 1) cp_async16(s_ring + (((u32)(next_c - 1) & 7u) << 4), gsrc - 16);
+                    if (want > 2) cp_async16(s_ring + (((u32)(next_c - 2) & 7u) << 4), gsrc - 32);
+                    next_c -= max(want, 0);
+                    cp_commit();
+                    pend2 = pend1;
+                    pend1 = next_c + 1;
+                    // lowest chunk the next four sequences can touch: 4 x 89 bits + 64-bit window + 31
+                    const i32 need_lo = max((P - 451) >> 7, 0);
+                    if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }     // rare: wait for everything
+                }
+                const u32 i0 = t * KZG_FSE_SERVICE;
+                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 1024);
+#pragma unroll
+                for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
+                    const u32 i = i0 + u;
+                    const bool act = i < nseq, notlast = i + 1 < nseq;
+                    const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
+                    u32 hi, lo;
+                    KZG_FSE_WINDOW(hi, lo);
+                    const u32 ofc = eOF & 63u;
+                    const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
+                    const u32 llb = pLL >> 24, mlb = pML >> 24;
+                    const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
+                    // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
+                    const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
+                    const u32 E = ofc + mlb + llb;
+                    wide |= act && E > KZG_FSE_WIDE_LIMIT;
+                    sts128(qb + u * 1024, hi, lo, pLL, pML);
+                    sts32(qb + u * 1024 + 16, ofc);
+                    // state bits sit right below the E extra bits (valid when E <= 32: E + 26 <= 58 bits)
+                    const u32 X = __funnelshift_lc(lo, hi, E);
+                    const u32 X2 = X << bLL, X3 = X2 << bML;
+                    sLL = (nLL << bLL) - szLL + __funnelshift_lc(X, 0u, bLL);
+                    sML = (nML << bML) - szML + __funnelshift_lc(X2, 0u, bML);
+                    sOF = (nOF << bOF) - szOF + __funnelshift_lc(X3, 0u, bOF);
+                    P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
+                }
+                __threadfence_block();
+                bar_arrive(BAR_FULL + buf);
+            }
+            cp_wait<0>();
+            // hand the verdict on the bitstream to the post warp: bit 0 = consumed exactly, bit 1 = general path needed
+            sts32(s_lane, (P == j.lowbits ? 1u : 0u) | (wide ? 2u : 0u));
+            bar_sync(BAR_PAIR);
+            if (cb && nseq && wide) {
+                j.nseq = nseq;
+                slow_decode(j, tLL, tML, tOF, s_llx, s_mlx, res);
+                cb->status_seq = res.status;
+                cb->regen = res.regen;
+                cb->lit_used = res.lit_used;
+                cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
+            }
+        } else {
+            // =================================================================== post warp
+            u32 rep0 = j.rep0, rep1 = j.rep1, rep2 = j.rep2;
+            u32 lit_end = 0, out_end = 0, ovf = 0;
+            u64* out = j.out;
+            for (u32 t = 0; t < nint; t++) {
+                const u32 buf = t & 1u;
+                bar_sync(BAR_FULL + buf);
+                const u32 i0 = t * KZG_FSE_SERVICE;
+                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 1024);
+#pragma unroll
+                for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
+                    const u32 i = i0 + u;
+                    const bool act = i < nseq;
+                    u32 hi, lo, pLL, pML;
+                    lds128(qb + u * 1024, hi, lo, pLL, pML);
+                    const u32 ofc = lds32(qb + u * 1024 + 16);
+                    const u32 llb = pLL >> 24, mlb = pML >> 24;
+                    const u32 ofx = __funnelshift_lc(hi, 0u, ofc);
+                    const u32 mlx_ = __funnelshift_lc(__funnelshift_l(lo, hi, ofc), 0u, mlb);
+                    const u32 llx_ = __funnelshift_lc(__funnelshift_lc(lo, hi, ofc + mlb), 0u, llb);
+                    const u32 ofv = (1u << ofc) + ofx;
+                    const u32 ml = act ? (pML & 0xFFFFFFu) + mlx_ : 0u;
+                    const u32 ll = act ? (pLL & 0xFFFFFFu) + llx_ : 0u;
+                    // repeat-offset history (Appendix A.6) with selects.  "rep0 - 1": a symbolic value counts its
+                    // decrement in bits [2,27) (+4), a concrete one just loses 1 (0 is rejected at execution).
+                    const bool isrep = ofc < 2u;                         // ofv in {1, 2, 3}
+                    const u32 idx = ofv - 1u + (ll == 0u ? 1u : 0u);     // meaningful when isrep
+                    const u32 dec = rep0 - 1u + (rep0 >> 27) * 5u;
+                    u32 cand = idx == 1u ? rep1 : rep0;
+                    cand = idx == 2u ? rep2 : cand;
+                    cand = idx == 3u ? dec : cand;
+                    const u32 off = isrep ? cand : min(ofv - 3u, (u32)KZG_OFF_INVALID);
+                    rep2 = ((isrep && idx <= 1u) || !act) ? rep2 : rep1;
+                    rep1 = ((isrep && idx == 0u) || !act) ? rep1 : rep0;
+                    rep0 = act ? off : rep0;
+                    lit_end += ll;
+                    out_end += ll + ml;
+                    ovf |= out_end;           // one sequence adds < 2^18, so any overflow past 2^18 leaves a high bit here
+                    if (act) out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
+                }
+                if (t + 2 < nint) {          // matched by the chain warp's wait two hand-overs later
+                    __threadfence_block();   // the queue reads above are performed before the buffer is handed back
+                    bar_arrive(BAR_EMPTY + buf);
+                }
+            }
+            bar_sync(BAR_PAIR);
+            const u32 verdict = lds32(s_lane);
+            if (cb && cb->status_seq == KZG_OK && cb->status_lit == KZG_OK && !(nseq && (verdict & 2u))) {
+                if (nseq && (verdict & 1u)) {
+                    j.lowbits = 0;
+                    finish_result(res, j, 0, lit_end, out_end, ovf, rep0, rep1, rep2);
+                }
+                cb->status_seq = res.status;
+                cb->regen = res.regen;
+                cb->lit_used = res.lit_used;
+                cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
             }
         }
 #undef KZG_FSE_WINDOW
-        cp_wait<0>();
-        __syncwarp();
-        if (cb && cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) {
-            if (nseq) {
-                if (wide) slow_decode(j, tLL, tML, tOF, s_llx, s_mlx, res);
-                else finish_result(res, j, P, lit_end, out_end, ovf, rep0, rep1, rep2);
-            }
-            cb->status_seq = res.status;
-            cb->regen = res.regen;
-            cb->lit_used = res.lit_used;
-            cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
-        }
-        __syncwarp();
+        bar_sync(BAR_PAIR);          // queue, ring, tables and hand-over words are free for the next round
     }
 }
