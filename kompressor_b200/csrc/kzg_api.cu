@@ -13,6 +13,9 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "kzg: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -(int)KZG_E_MEMORY; } } while (0)
 
+#define KZG_MAX_CHUNKS 32                 // host-pointer API: sub-batches pipelined over the copy engines
+#define KZG_CHUNK_BYTES (128ull << 20)   // target decoded bytes per sub-batch: big enough that a sub-batch still fills the GPU
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -37,9 +40,11 @@ struct kzg_ctx {
     u64 block_cap = 0, cblock_cap = 0, lit_cap = 0, seq_cap = 0;
     u32 tile_bytes = 0;
     double lit_factor = 0.75, seq_div = 12.0, block_div = 32768.0;
-    KzgCounters* h_ctr = nullptr;   // pinned
+    KzgCounters* h_ctr = nullptr;   // pinned, KZG_MAX_CHUNKS slots (slot 0 = the device-pointer API)
     cudaStream_t last_stream = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr;                 // host-pointer API: decode stream
+    cudaStream_t in_stream = nullptr, out_stream = nullptr;   // host-pointer API: H2D / D2H copy streams
+    cudaEvent_t ev_in[KZG_MAX_CHUNKS] = {}, ev_cmp[KZG_MAX_CHUNKS] = {}, ev_tab = nullptr;
     u32 last_launches = 0;
     u64 last_n_frames = 0;
     // staging for the host-pointer form
@@ -117,9 +122,16 @@ extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
     c->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) fprintf(stderr, "kzg: warning: built for sm_100a, device is sm_%d%d\n", prop.major, prop.minor);
-    if (cudaMallocHost((void**)&c->h_ctr, sizeof(KzgCounters)) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
-    memset(c->h_ctr, 0, sizeof(KzgCounters));
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFreeHost(c->h_ctr); delete c; return (int)KZG_E_MEMORY; }
+    if (cudaMallocHost((void**)&c->h_ctr, KZG_MAX_CHUNKS * sizeof(KzgCounters)) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
+    memset(c->h_ctr, 0, KZG_MAX_CHUNKS * sizeof(KzgCounters));
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_tab, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < KZG_MAX_CHUNKS; i++)
+        ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); kzg_ctx_destroy(c); return (int)KZG_E_MEMORY; }
     // constants: default FSE descriptor + packed code tables
     struct { KzgFseDesc d; u32 codes[96]; } hc;
     memset(&hc, 0, sizeof hc);
@@ -142,6 +154,10 @@ extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     for (DevBuf* b : all) b->release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->in_stream) cudaStreamDestroy(c->in_stream);
+    if (c->out_stream) cudaStreamDestroy(c->out_stream);
+    if (c->ev_tab) cudaEventDestroy(c->ev_tab);
+    for (int i = 0; i < KZG_MAX_CHUNKS; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_cmp[i]) cudaEventDestroy(c->ev_cmp[i]); }
     for (int i = 0; i <= KZG_N_STAGES; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
 }
@@ -245,20 +261,12 @@ static int ensure_workspace(kzg_ctx* c, u64 n_frames, u64 total_src, u64 total_d
     return 0;
 }
 
-extern "C" int kzg_decompress_batch_device(kzg_ctx* c, const void* d_src, const uint64_t* d_src_off,
-                                           const uint64_t* d_src_size, void* d_dst, const uint64_t* d_dst_off,
-                                           const uint64_t* d_dst_cap, uint64_t n_frames, uint64_t total_src_bytes,
-                                           uint64_t total_dst_cap, uint64_t max_frame_dst_cap, uint32_t* d_status,
-                                           uint64_t* d_out_size, void* cuda_stream) {
-    if (!c) return -(int)KZG_E_GENERIC;
-    if (n_frames > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
-    std::lock_guard<std::mutex> lock(c->mu);
-    CK(cudaSetDevice(c->device));
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
-    c->last_stream = stream;
-    c->last_n_frames = n_frames;
-    c->last_launches = 0;
-    if (n_frames == 0) return 0;
+// Enqueues one batch on `stream` (context already locked / device set).  The batch's counters are copied to
+// pinned slot `slot` when it finishes.  Returns kernels launched or a negative code.
+static int enqueue_batch(kzg_ctx* c, const void* d_src, const uint64_t* d_src_off, const uint64_t* d_src_size, void* d_dst,
+                         const uint64_t* d_dst_off, const uint64_t* d_dst_cap, uint64_t n_frames, uint64_t total_src_bytes,
+                         uint64_t total_dst_cap, uint64_t max_frame_dst_cap, uint32_t* d_status, uint64_t* d_out_size,
+                         cudaStream_t stream, int slot) {
     if (ensure_workspace(c, n_frames, total_src_bytes, total_dst_cap, max_frame_dst_cap)) return -(int)KZG_E_MEMORY;
     KzgBatch b;
     memset(&b, 0, sizeof b);
@@ -281,9 +289,39 @@ extern "C" int kzg_decompress_batch_device(kzg_ctx* c, const void* d_src, const 
     const int launches = kzg_launch_batch(b, c->sm_count, stream, c->profiling ? c->ev : nullptr);
     c->ev_valid = c->profiling;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_ctr, c->ctr.p, sizeof(KzgCounters), cudaMemcpyDeviceToHost, stream));
-    c->last_launches = (u32)launches;
+    CK(cudaMemcpyAsync(c->h_ctr + slot, c->ctr.p, sizeof(KzgCounters), cudaMemcpyDeviceToHost, stream));
     return launches;
+}
+
+extern "C" int kzg_decompress_batch_device(kzg_ctx* c, const void* d_src, const uint64_t* d_src_off,
+                                           const uint64_t* d_src_size, void* d_dst, const uint64_t* d_dst_off,
+                                           const uint64_t* d_dst_cap, uint64_t n_frames, uint64_t total_src_bytes,
+                                           uint64_t total_dst_cap, uint64_t max_frame_dst_cap, uint32_t* d_status,
+                                           uint64_t* d_out_size, void* cuda_stream) {
+    if (!c) return -(int)KZG_E_GENERIC;
+    if (n_frames > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    c->last_stream = stream;
+    c->last_n_frames = n_frames;
+    c->last_launches = 0;
+    if (n_frames == 0) return 0;
+    const int launches = enqueue_batch(c, d_src, d_src_off, d_src_size, d_dst, d_dst_off, d_dst_cap, n_frames, total_src_bytes,
+                                       total_dst_cap, max_frame_dst_cap, d_status, d_out_size, stream, 0);
+    if (launches > 0) c->last_launches = (u32)launches;
+    return launches;
+}
+
+// Grows the workspace after an overflow reported in counters `k`.
+static void grow_after_overflow(kzg_ctx* c, const KzgCounters& k) {
+    if (k.overflow & 3u) {
+        const u64 need = (u64)(k.n_blocks > k.n_cblocks ? k.n_blocks : k.n_cblocks) + 64;
+        c->block_cap = c->cblock_cap = need > c->block_cap * 2 ? need : c->block_cap * 2;
+    }
+    if (k.overflow & 4u) { const u64 w = k.lit_used + (k.lit_used >> 4) + 4096; if (w > c->lit_cap) c->lit_cap = w; }
+    if (k.overflow & 8u) { const u64 w = k.seq_used + (k.seq_used >> 4) + 4096; if (w > c->seq_cap) c->seq_cap = w; }
+    if (k.overflow & 16u) c->tile_bytes = KZG_BLOCK_MAX + 64;
 }
 
 extern "C" int kzg_batch_finish(kzg_ctx* c) {
@@ -292,15 +330,9 @@ extern "C" int kzg_batch_finish(kzg_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->last_stream));
     if (c->last_n_frames == 0) return 0;
-    const KzgCounters& k = *c->h_ctr;
+    const KzgCounters& k = c->h_ctr[0];
     if (!k.overflow) return 0;
-    if (k.overflow & 3u) {
-        const u64 need = (u64)(k.n_blocks > k.n_cblocks ? k.n_blocks : k.n_cblocks) + 64;
-        c->block_cap = c->cblock_cap = need > c->block_cap * 2 ? need : c->block_cap * 2;
-    }
-    if (k.overflow & 4u) c->lit_cap = k.lit_used + (k.lit_used >> 4) + 4096;
-    if (k.overflow & 8u) c->seq_cap = k.seq_used + (k.seq_used >> 4) + 4096;
-    if (k.overflow & 16u) c->tile_bytes = KZG_BLOCK_MAX + 64;
+    grow_after_overflow(c, k);
     return 1;
 }
 
@@ -345,26 +377,23 @@ extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint
                                          uint32_t* status, uint64_t* out_size) {
     if (!c) return -(int)KZG_E_GENERIC;
     if (n == 0) return 0;
+    if (n > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(c->mu);
     CK(cudaSetDevice(c->device));
-    // extent of the source / destination spans and sizing sums
-    u64 src_lo = ~0ull, src_hi = 0, dst_lo = ~0ull, dst_hi = 0, tot_src = 0, tot_dst = 0, max_dst = 0;
+    // extent of the source / destination spans
+    u64 src_lo = ~0ull, src_hi = 0, dst_lo = ~0ull, dst_hi = 0, tot_dst = 0;
     for (u64 i = 0; i < n; i++) {
         if (src_off[i] < src_lo) src_lo = src_off[i];
         if (src_off[i] + src_size[i] > src_hi) src_hi = src_off[i] + src_size[i];
         if (dst_off[i] < dst_lo) dst_lo = dst_off[i];
         if (dst_off[i] + dst_cap[i] > dst_hi) dst_hi = dst_off[i] + dst_cap[i];
-        tot_src += src_size[i]; tot_dst += dst_cap[i];
-        if (dst_cap[i] > max_dst) max_dst = dst_cap[i];
+        tot_dst += dst_cap[i];
     }
     const u64 src_span = src_hi - src_lo, dst_span = dst_hi - dst_lo;
     // device staging: [src span | pad], [dst span], tables: off/size/doff/dcap (u64 each) + out_size (u64) + status (u32)
     const u64 tab_bytes = n * (5 * 8 + 4);
-    {
-        std::lock_guard<std::mutex> lock(c->mu);
-        if (c->st_src.ensure(src_span + 64) || c->st_dst.ensure(dst_span + 64) || c->st_tab.ensure(tab_bytes + 64))
-            return -(int)KZG_E_MEMORY;
-    }
-    cudaStream_t s = c->own_stream;
+    if (c->st_src.ensure(src_span + 64) || c->st_dst.ensure(dst_span + 64) || c->st_tab.ensure(tab_bytes + 64))
+        return -(int)KZG_E_MEMORY;
     u64* t_off = (u64*)c->st_tab.p;
     u64* t_size = t_off + n;
     u64* t_doff = t_size + n;
@@ -378,31 +407,79 @@ extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint
         h_tab[i] = src_off[i] - src_lo; h_tab[n + i] = src_size[i];
         h_tab[2 * n + i] = dst_off[i] - dst_lo; h_tab[3 * n + i] = dst_cap[i];
     }
+    // Sub-batches of consecutive frames, pipelined over three streams: while sub-batch k is decoded, the
+    // compressed bytes of k+1 are on their way in and the output of k-1 is on its way out (the two PCIe
+    // directions and the SMs all busy at once).  The kernels of successive sub-batches run back to back on one
+    // stream, so they can share the workspace.
+    u64 nchunks = (tot_dst + KZG_CHUNK_BYTES - 1) / KZG_CHUNK_BYTES;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > KZG_MAX_CHUNKS) nchunks = KZG_MAX_CHUNKS;
+    if (nchunks > n) nchunks = n;
+    u64 bounds[KZG_MAX_CHUNKS + 1];
+    {
+        u64 acc = 0, k = 0;
+        bounds[0] = 0;
+        for (u64 i = 0; i < n && k + 1 < nchunks; i++) {
+            acc += dst_cap[i];
+            if (acc * nchunks >= tot_dst * (k + 1)) bounds[++k] = i + 1;
+        }
+        while (k < nchunks) bounds[++k] = n;
+    }
+    cudaStream_t s_in = c->in_stream, s_cmp = c->own_stream, s_out = c->out_stream;
+    c->last_stream = s_cmp;
+    c->last_n_frames = n;
     int rc = 0;
+    u32 launches_total = 0;
     for (int attempt = 0; attempt < 4; attempt++) {
-        if (cudaMemcpyAsync(c->st_tab.p, h_tab, n * 4 * 8, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-            cudaMemcpyAsync(c->st_src.p, (const u8*)src + src_lo, src_span, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = -(int)KZG_E_MEMORY; break; }
-        rc = kzg_decompress_batch_device(c, c->st_src.p, t_off, t_size, c->st_dst.p, t_doff, t_dcap, n, tot_src, tot_dst,
-                                         max_dst, t_status, t_osize, s);
+        bool ok = cudaMemcpyAsync(c->st_tab.p, h_tab, n * 4 * 8, cudaMemcpyHostToDevice, s_in) == cudaSuccess &&
+                  cudaEventRecord(c->ev_tab, s_in) == cudaSuccess && cudaStreamWaitEvent(s_cmp, c->ev_tab, 0) == cudaSuccess;
+        launches_total = 0;
+        rc = 0;
+        for (u64 k = 0; ok && k < nchunks; k++) {
+            const u64 f0 = bounds[k], f1 = bounds[k + 1];
+            if (f1 <= f0) { cudaEventRecord(c->ev_in[k], s_in); cudaEventRecord(c->ev_cmp[k], s_cmp); continue; }
+            // compressed bytes of this sub-batch: the span its frames cover
+            u64 lo = ~0ull, hi = 0, cs = 0, cd = 0, md = 0;
+            for (u64 i = f0; i < f1; i++) {
+                if (src_off[i] < lo) lo = src_off[i];
+                if (src_off[i] + src_size[i] > hi) hi = src_off[i] + src_size[i];
+                cs += src_size[i]; cd += dst_cap[i];
+                if (dst_cap[i] > md) md = dst_cap[i];
+            }
+            ok = cudaMemcpyAsync((u8*)c->st_src.p + (lo - src_lo), (const u8*)src + lo, hi - lo, cudaMemcpyHostToDevice, s_in) == cudaSuccess &&
+                 cudaEventRecord(c->ev_in[k], s_in) == cudaSuccess && cudaStreamWaitEvent(s_cmp, c->ev_in[k], 0) == cudaSuccess;
+            if (!ok) break;
+            const int l = enqueue_batch(c, c->st_src.p, t_off + f0, t_size + f0, c->st_dst.p, t_doff + f0, t_dcap + f0, f1 - f0, cs, cd, md,
+                                        t_status + f0, t_osize + f0, s_cmp, (int)k);
+            if (l < 0) { rc = l; break; }
+            launches_total += (u32)l;
+            ok = cudaEventRecord(c->ev_cmp[k], s_cmp) == cudaSuccess && cudaStreamWaitEvent(s_out, c->ev_cmp[k], 0) == cudaSuccess;
+            // copy back only the caller's capacity regions of this sub-batch, coalescing adjacent ones into runs
+            u64 run_lo = dst_off[f0], run_hi = dst_off[f0] + dst_cap[f0];
+            for (u64 i = f0 + 1; ok && i <= f1; i++) {
+                if (i < f1 && dst_off[i] == run_hi) { run_hi += dst_cap[i]; continue; }
+                if (run_hi > run_lo)
+                    ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)c->st_dst.p + (run_lo - dst_lo), run_hi - run_lo,
+                                         cudaMemcpyDeviceToHost, s_out) == cudaSuccess;
+                if (i < f1) { run_lo = dst_off[i]; run_hi = dst_off[i] + dst_cap[i]; }
+            }
+        }
+        if (rc == 0 && ok)
+            ok = cudaMemcpyAsync(status, t_status, n * 4, cudaMemcpyDeviceToHost, s_out) == cudaSuccess &&
+                 cudaMemcpyAsync(out_size, t_osize, n * 8, cudaMemcpyDeviceToHost, s_out) == cudaSuccess;
+        const bool synced = cudaStreamSynchronize(s_in) == cudaSuccess && cudaStreamSynchronize(s_cmp) == cudaSuccess &&
+                            cudaStreamSynchronize(s_out) == cudaSuccess;
         if (rc < 0) break;
-        rc = kzg_batch_finish(c);
-        if (rc <= 0) break;
+        if (!ok || !synced) { cudaGetLastError(); rc = -(int)KZG_E_MEMORY; break; }
+        // optimistic workspace sizing: any sub-batch that overflowed makes the whole call run again, larger
+        bool again = false;
+        for (u64 k = 0; k < nchunks; k++)
+            if (bounds[k + 1] > bounds[k] && c->h_ctr[k].overflow) { grow_after_overflow(c, c->h_ctr[k]); again = true; }
+        if (!again) break;
+        rc = 1;
     }
     if (rc == 1) rc = -(int)KZG_E_MEMORY;
-    if (rc == 0) {
-        bool ok = cudaMemcpyAsync(status, t_status, n * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-                  cudaMemcpyAsync(out_size, t_osize, n * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess;
-        // copy back only the caller's capacity regions, coalescing adjacent ones into runs
-        u64 run_lo = dst_off[0], run_hi = dst_off[0] + dst_cap[0];
-        for (u64 i = 1; ok && i <= n; i++) {
-            if (i < n && dst_off[i] == run_hi) { run_hi += dst_cap[i]; continue; }
-            if (run_hi > run_lo)
-                ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)c->st_dst.p + (run_lo - dst_lo), run_hi - run_lo,
-                                     cudaMemcpyDeviceToHost, s) == cudaSuccess;
-            if (i < n) { run_lo = dst_off[i]; run_hi = dst_off[i] + dst_cap[i]; }
-        }
-        if (!ok || cudaStreamSynchronize(s) != cudaSuccess) rc = -(int)KZG_E_MEMORY;
-    }
+    c->last_launches = launches_total;
     free(h_tab);
     return rc;
 }
