@@ -35,7 +35,7 @@ struct kzg_ctx {
     int device = 0;
     int sm_count = 0;
     std::mutex mu;
-    DevBuf frames, blocks, cblocks, fse, huf, hlist, slist, lit, seq, ctr, consts;
+    DevBuf frames, blocks, cblocks, fse, huf, hlist, slist, lit, seq, fsetab, ctr, consts;
     // sizing state (sticky across batches, grown on overflow)
     u64 block_cap = 0, cblock_cap = 0, lit_cap = 0, seq_cap = 0;
     u32 tile_bytes = 0;
@@ -149,7 +149,7 @@ extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
 extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* all[] = { &c->frames, &c->blocks, &c->cblocks, &c->fse, &c->huf, &c->hlist, &c->slist, &c->lit, &c->seq,
+    DevBuf* all[] = { &c->frames, &c->blocks, &c->cblocks, &c->fse, &c->huf, &c->hlist, &c->slist, &c->lit, &c->seq, &c->fsetab,
                       &c->ctr, &c->consts, &c->st_src, &c->st_dst, &c->st_tab, &c->dict };
     for (DevBuf* b : all) b->release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -256,7 +256,8 @@ static int ensure_workspace(kzg_ctx* c, u64 n_frames, u64 total_src, u64 total_d
     if (c->frames.ensure(n_frames * sizeof(KzgFrame)) || c->blocks.ensure(c->block_cap * sizeof(KzgBlock)) ||
         c->cblocks.ensure(c->cblock_cap * sizeof(KzgCBlock)) || c->fse.ensure(c->cblock_cap * sizeof(KzgFseDesc)) ||
         c->huf.ensure(c->cblock_cap * sizeof(KzgHufDesc)) || c->hlist.ensure(c->cblock_cap * 4) ||
-        c->slist.ensure(c->cblock_cap * 4) || c->lit.ensure(c->lit_cap + 64) || c->seq.ensure(c->seq_cap * 8))
+        c->slist.ensure(c->cblock_cap * 4) || c->lit.ensure(c->lit_cap + 64) || c->seq.ensure(c->seq_cap * 8) ||
+        c->fsetab.ensure(c->cblock_cap * 2560 + 64))
         return -1;
     return 0;
 }
@@ -278,7 +279,7 @@ static int enqueue_batch(kzg_ctx* c, const void* d_src, const uint64_t* d_src_of
     b.frames = (KzgFrame*)c->frames.p; b.blocks = (KzgBlock*)c->blocks.p; b.cblocks = (KzgCBlock*)c->cblocks.p;
     b.fse = (KzgFseDesc*)c->fse.p; b.huf = (KzgHufDesc*)c->huf.p;
     b.hlist = (u32*)c->hlist.p; b.slist = (u32*)c->slist.p;
-    b.lit_pool = (u8*)c->lit.p; b.seq_pool = (u64*)c->seq.p;
+    b.lit_pool = (u8*)c->lit.p; b.seq_pool = (u64*)c->seq.p; b.fse_tab = (u16*)c->fsetab.p;
     b.ctr = (KzgCounters*)c->ctr.p;
     b.fse_default = (const KzgFseDesc*)c->consts.p;
     b.code_tables = (const u32*)((const u8*)c->consts.p + sizeof(KzgFseDesc));
@@ -365,7 +366,7 @@ extern "C" int kzg_last_batch_stats(kzg_ctx* c, kzg_batch_stats* out) {
     out->n_blocks = k.n_blocks; out->n_cblocks = k.n_cblocks; out->n_hblocks = k.n_hblocks; out->n_sblocks = k.n_sblocks;
     out->lit_bytes = k.lit_used; out->seq_records = k.seq_used;
     out->workspace_bytes = c->frames.cap + c->blocks.cap + c->cblocks.cap + c->fse.cap + c->huf.cap + c->hlist.cap +
-                           c->slist.cap + c->lit.cap + c->seq.cap;
+                           c->slist.cap + c->lit.cap + c->seq.cap + c->fsetab.cap;
     out->launches = c->last_launches; out->tile_bytes = c->tile_bytes; out->sm_count = (u32)c->sm_count;
     out->overflow = k.overflow;
     return 0;

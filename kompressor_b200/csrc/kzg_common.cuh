@@ -164,6 +164,7 @@ struct KzgBatch {
     u32* slist;         // compressed blocks with sequences
     u8* lit_pool;
     u64* seq_pool;
+    u16* fse_tab;       // built FSE decode tables, 1280 cells (LL 512 | ML 512 | OF 256) per entry of slist
     KzgCounters* ctr;
     const KzgFseDesc* fse_default;
     const u32* code_tables;   // 36 LL + 53 ML packed (extra_bits << 24 | baseline)

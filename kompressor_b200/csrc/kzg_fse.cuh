@@ -13,8 +13,8 @@
 //     named barriers (bar.arrive / bar.sync), never by spinning;
 //   * tables live in shared memory, interleaved by lane: cell i of lane L is the u16 at byte
 //     (i << 6) + (L << 1) of the pair's table area, so a lookup costs one multiply-add and lanes collide
-//     at most pairwise (two lanes share a 32-bit bank column); the chain warp builds the LL and OF tables
-//     while the post warp builds ML;
+//     at most pairwise (two lanes share a 32-bit bank column); the tables are built once per block by
+//     kzg_fsetab_kernel (warp-parallel) and only copied in here, LL and OF by the chain warp, ML by the post warp;
 //   * the backward bitstream is staged by cp.async (LDGSTS, no destination register, so no per-warp
 //     scoreboard stall) into a per-lane ring of eight 16-byte chunks (128 contiguous bytes per lane);
 //     copies are issued only at warp-uniform points (every 4 sequences), sized so that the ring always
@@ -36,11 +36,10 @@
 #define KZG_FSE_TAB_BYTES (KZG_FSE_CELLS * 64)              // per pair: 32 lanes x 1280 cells x 2 B
 #define KZG_FSE_RING_CHUNKS 8
 #define KZG_FSE_RING_BYTES (KZG_FSE_RING_CHUNKS * 512)      // per pair: 32 lanes x (8 chunks x 16 B, contiguous per lane)
-#define KZG_FSE_SCR_BYTES 4096                              // per pair: table-build scratch of the post warp
 #define KZG_FSE_SERVICE 4                                   // sequences per hand-over / between ring service points
 #define KZG_FSE_Q_BYTES (2 * KZG_FSE_SERVICE * 1024)        // per pair: 2 buffers x 4 sequences x 32 lanes x 32 B
 #define KZG_FSE_MISC_BYTES 512                              // per pair: ticket, trip count, per-lane hand-over words
-#define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_SCR_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
+#define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
 #define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
 #ifndef KZG_FSE_WIDE_LIMIT
@@ -69,55 +68,18 @@ __device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// Per-lane scratch during the table build = the lane's (still idle) bitstream ring: 64 u16.
-__device__ __forceinline__ u32 scr_addr(u32 ring, u32 j) { return ring + (j << 1); }
-
-// Builds one decode table in the lane's column. Cell = symbol | next << 6 (see kzg_entropy.cuh).
-// tab: shared address of the lane's cell 0 of this table; ring: shared address of the lane's ring.
-__device__ __forceinline__ u32 build_table(u32 tab, u32 ring, const KzgFseDesc* d, u32 t) {
-    if (d->kind[t] == 1) { sts16(tab, (1u << 6) | (u32)(u16)d->norm[t][0]); return 0; }
-    const u32 log = d->log[t], nsym = d->nsym[t];
-    const u32 size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
-    const i16* norm = d->norm[t];
-    u32 high = size;
-    for (u32 s = 0; s < nsym; s++) {
-        const i32 c = norm[s];
-        u32 v = (u32)c & 0x7FFFu;
-        if (c < 0) { high--; sts16(tab + (high << 6), s); v = 0x8001u; }
-        sts16(scr_addr(ring, s), v);
+// Copies one built table (2^log cells, contiguous in the workspace) into the lane's column of the interleaved
+// shared-memory layout: 16-byte loads, eight 2-byte scattered stores each.  Iterations are independent.
+__device__ __forceinline__ void load_table(u32 tab, const u16* g, u32 log) {
+    const u32 nvec = max(1u << log, 8u) >> 3;
+    const uint4* g4 = reinterpret_cast<const uint4*>(g);
+#pragma unroll 4
+    for (u32 q = 0; q < nvec; q++) {
+        const uint4 v = __ldg(g4 + q);
+        const u32 a = tab + (q << 9);
+        sts16(a, v.x); sts16(a + 64, v.x >> 16); sts16(a + 128, v.y); sts16(a + 192, v.y >> 16);
+        sts16(a + 256, v.z); sts16(a + 320, v.z >> 16); sts16(a + 384, v.w); sts16(a + 448, v.w >> 16);
     }
-    // spread: one flat loop over the (high) cells that are not "less than one" symbols
-    {
-        u32 pos = 0, s = 0, rem = 0;
-        for (u32 j = 0; j < high; j++) {
-            while (rem == 0 && s < 64u) {
-                const u32 v = lds16(scr_addr(ring, s));
-                rem = (v & 0x8000u) ? 0u : v;
-                s++;
-            }
-            sts16(tab + (pos << 6), s - 1);
-            rem--;
-            do { pos = (pos + step) & mask; } while (pos >= high);
-        }
-    }
-    // numbering pass, four cells at a time: the loads of a group are independent, so the shared-memory
-    // latency is paid once per group instead of once per cell; cells of a group that share a symbol are
-    // counted by comparison, and the counters are stored in order so the last duplicate wins
-    for (u32 i = 0; i < size; i += 4) {
-        const u32 a = tab + (i << 6);
-        const u32 s0 = lds16(a), s1 = lds16(a + 64), s2 = lds16(a + 128), s3 = lds16(a + 192);
-        const u32 a0 = scr_addr(ring, s0), a1 = scr_addr(ring, s1), a2 = scr_addr(ring, s2), a3 = scr_addr(ring, s3);
-        const u32 v0 = lds16(a0);
-        const u32 v1 = lds16(a1) + (s1 == s0);
-        const u32 v2 = lds16(a2) + (s2 == s0) + (s2 == s1);
-        const u32 v3 = lds16(a3) + (s3 == s0) + (s3 == s1) + (s3 == s2);
-        sts16(a0, v0 + 1); sts16(a1, v1 + 1); sts16(a2, v2 + 1); sts16(a3, v3 + 1);
-        sts16(a, ((v0 & 0x7FFFu) << 6) | s0);
-        sts16(a + 64, ((v1 & 0x7FFFu) << 6) | s1);
-        sts16(a + 128, ((v2 & 0x7FFFu) << 6) | s2);
-        sts16(a + 192, ((v3 & 0x7FFFu) << 6) | s3);
-    }
-    return log;
 }
 
 // Generic (slow, rare) backward bit read straight from global memory: n <= 32 bits below position P.
@@ -216,9 +178,8 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
     const u32 s_pair = s_llx + KZG_FSE_CODE_WORDS * 4 + pair * KZG_FSE_PAIR_SMEM;
     const u32 s_tab = s_pair + (lane << 1);
     const u32 s_ring = s_pair + KZG_FSE_TAB_BYTES + (lane << 7);
-    const u32 s_scr = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + (lane << 7);
-    const u32 s_q = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_SCR_BYTES + (lane << 5);
-    const u32 s_misc = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_SCR_BYTES + KZG_FSE_Q_BYTES;
+    const u32 s_q = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + (lane << 5);
+    const u32 s_misc = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES;
     const u32 s_lane = s_misc + 64 + (lane << 2);           // per-lane hand-over word
     const u32 tLL = s_tab, tML = s_tab + (512u << 6), tOF = s_tab + (1024u << 6);
     // barrier ids of this pair (0 is __syncthreads)
@@ -241,18 +202,19 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
             cb = &B.cblocks[B.slist[si]];
             if (cb->status_seq == KZG_OK && cb->status_lit == KZG_OK) j.nseq = cb->n_seq;
         }
-        // ---- tables, in the lane's column: the chain warp builds LL and OF (scratch = its idle ring), the
-        // post warp builds ML.  Idle lanes get one-cell tables so the straight-line loop stays in bounds.
+        // ---- tables (built by kzg_fsetab_kernel) into the lane's column: the chain warp loads LL and OF, the
+        // post warp ML.  Idle lanes get one-cell tables so the straight-line loop stays in bounds.
         if (j.nseq) {
             const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-            if (chain) {
-                j.logLL = build_table(tLL, s_ring, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0);
-                j.logOF = build_table(tOF, s_ring, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1);
-                const KzgFseDesc* d2 = o2 == KZG_NONE ? B.fse_default : &B.fse[o2];
-                j.logML = d2->kind[2] == 1 ? 0u : (u32)d2->log[2];
-            } else {
-                j.logML = build_table(tML, s_scr, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2);
-            }
+            const KzgFseDesc* d0 = o0 == KZG_NONE ? B.fse_default : &B.fse[o0];
+            const KzgFseDesc* d1 = o1 == KZG_NONE ? B.fse_default : &B.fse[o1];
+            const KzgFseDesc* d2 = o2 == KZG_NONE ? B.fse_default : &B.fse[o2];
+            j.logLL = d0->kind[0] == 1 ? 0u : (u32)d0->log[0];
+            j.logOF = d1->kind[1] == 1 ? 0u : (u32)d1->log[1];
+            j.logML = d2->kind[2] == 1 ? 0u : (u32)d2->log[2];
+            const u16* gt = B.fse_tab + (size_t)si * KZG_FSE_CELLS;
+            if (chain) { load_table(tLL, gt, j.logLL); load_table(tOF, gt + 1024, j.logOF); }
+            else load_table(tML, gt + 512, j.logML);
             j.lit_regen = cb->lit_regen;
             j.block_max = B.frames[cb->frame].block_max;
             j.out = B.seq_pool + cb->seq_out;

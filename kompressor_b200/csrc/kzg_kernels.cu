@@ -5,6 +5,7 @@
 //   parse     thread / block        literals + sequences section headers, Huffman weights,
 //                                   FSE normalised counts, pool allocation                   (s3/s4 headers)
 //   link      thread / frame        treeless / repeat-mode table owners inside a frame
+//   fsetab    warp / block          the three FSE decode tables of every block with sequences        (s4 tables)
 //   huffman   thread / stream       table build (4 lanes per table) + 4-stream literal decode (s3)
 //   fse       thread / block        table build + sequential ZSTD_decodeSequence state machine (s4)
 //   offsets   thread / frame        per-block output offsets, repeat-offset hand-over, size checks
@@ -17,6 +18,7 @@
 #include "kzg_kernels.cuh"
 #include "kzg_stages.cuh"
 #include "kzg_huf.cuh"
+#include "kzg_fsetab.cuh"
 #include "kzg_fse.cuh"
 #include "kzg_exec.cuh"
 
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
 // ------------------------------------------------------------------------------------------------
 static bool g_attr_done = false;
 
-const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "huffman", "fse", "offsets", "execute", "finish" };
+const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fsetab", "huffman", "fse", "offsets", "execute", "finish" };
 
 int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
     const size_t huf_smem = KZG_HUF_SMEM;
@@ -167,6 +169,8 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
     kzg_parse_kernel<<<pgrid ? pgrid : 1, 64, 0, stream>>>(b);
     KZG_MARK();
     kzg_link_kernel<<<fgrid, 128, 0, stream>>>(b);
+    KZG_MARK();
+    kzg_fsetab_kernel<<<sm_count * 8, KZG_TAB_WARPS * 32, 0, stream>>>(b);
     KZG_MARK();
     kzg_huf_kernel<<<sm_count * 3, KZG_HUF_WARPS * 32, huf_smem, stream>>>(b);
     KZG_MARK();
