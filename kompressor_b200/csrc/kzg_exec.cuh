@@ -149,7 +149,7 @@ __device__ __forceinline__ u32 hist_byte(const Win& w, i32 p) {
 
 // Flushes positions [w.F, upto) as 16-byte vectors; with `all`, also the ragged tail (bytes).
 __device__ __forceinline__ void flush(Win& w, i32 upto, bool all, u32 lane) {
-    if ((uintptr_t)(w.out + w.F) & 15) {      // unaligned start (block start, or after a warp-wide copy)
+    if (__builtin_expect(((uintptr_t)(w.out + w.F) & 15) != 0, 0)) {      // unaligned start (block start, or after a warp-wide copy)
         const i32 nh = min(upto - w.F, (i32)(16 - ((uintptr_t)(w.out + w.F) & 15)));
         if (!all && w.F + nh > upto) return;
         if ((i32)lane < nh) w.out[w.F + (i32)lane] = (u8)lds8(w.tile + (u32)(w.F - w.T0) + lane);
@@ -160,7 +160,7 @@ __device__ __forceinline__ void flush(Win& w, i32 upto, bool all, u32 lane) {
         uint4* g = reinterpret_cast<uint4*>(w.out + w.F);
         const u32 t = w.tile + (u32)(w.F - w.T0);
         if ((i32)lane < nvec) g[lane] = lds128(t + (lane << 4));
-        if (nvec > 32) {
+        if (__builtin_expect(nvec > 32, 0)) {
 #pragma unroll 1
             for (i32 v = (i32)lane + 32; v < nvec; v += 32) g[v] = lds128(t + ((u32)v << 4));
         }
@@ -202,7 +202,7 @@ __device__ __forceinline__ bool stage_literals(u32 stage, const u8* lit, u32 l0,
     const u32 nch = (a + (l1 - l0) + 15u) >> 4;             // <= 66
     g0 -= a;
     if (lane < nch) cp_async16(stage + (lane << 4), g0 + (lane << 4));
-    if (nch > 32) {
+    if (__builtin_expect(nch > 32, 0)) {
 #pragma unroll 1
         for (u32 c = lane + 32; c < nch; c += 32) cp_async16(stage + (c << 4), g0 + ((size_t)c << 4));
     }
@@ -274,12 +274,12 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         const bool bad = valid && (off - 1u >= KZG_OFF_INVALID - 1u || off > hist_before_block + mdst);
         const bool islong = ll > KZG_EX_LONG || ml > KZG_EX_LONG;
         const u32 longm = __ballot_sync(0xFFFFFFFFu, islong);
-        if (__any_sync(0xFFFFFFFFu, bad)) { err = true; break; }
+        if (__builtin_expect(__any_sync(0xFFFFFFFFu, bad), 0)) { err = true; break; }
         const i32 spos = (i32)mdst - (i32)off;
         const i32 be = (i32)((u32)(carry >> 46));
         // make room for the whole batch first if it fits a window (the usual case), so that the source
         // classification below sees the window it will run with
-        if (longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
+        if (__builtin_expect(longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE, 0)) slide(w, cur, lane);
 
         // ---- matches whose source is not (entirely) inside the window any more but has been flushed: stage the
         // 16-byte chunks covering it now.  (Tv and F only grow, so the classification stays true.)
@@ -308,7 +308,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         // One group of lanes (`mine`), whose output ends at block position ge and fits the window.
         auto run_group = [&](bool mine, i32 ge) {
             // ---- literal runs of the group (no dependencies)
-            if (this_staged || lfill) {
+            if (__builtin_expect(this_staged || lfill, 1)) {
                 lane_copy(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lsrc, lfill, rle);
             } else if (mine) {       // literal range too large to stage (rare): straight from global memory
                 const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
@@ -330,7 +330,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 const bool go = pending && need <= fin;
                 if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
                 lane_copy(da, (go && !slow) ? ml : 0u, sa, false, 0u);
-                if (anyslow) {
+                if (__builtin_expect(anyslow, 0)) {
                     if (go && slow) {     // short period, or a source straddling the flushed / window boundary: bytes in order
                         for (u32 k = 0; k < ml; k++) {
                             const i32 p = spos + (i32)k;
@@ -346,7 +346,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
             flush(w, cur, false, lane);
         };
 
-        if (longm == 0 && (u32)(be - cur) <= KZG_EX_CAP) {
+        if (__builtin_expect(longm == 0 && (u32)(be - cur) <= KZG_EX_CAP, 1)) {
             run_group(valid, be);                       // the usual case: the whole batch at once
         } else {
             u32 todo = nvalid == 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);     // lanes not yet executed, in order
