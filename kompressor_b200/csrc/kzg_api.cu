@@ -412,19 +412,26 @@ extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint
     // compressed bytes of k+1 are on their way in and the output of k-1 is on its way out (the two PCIe
     // directions and the SMs all busy at once).  The kernels of successive sub-batches run back to back on one
     // stream, so they can share the workspace.
-    u64 nchunks = (tot_dst + KZG_CHUNK_BYTES - 1) / KZG_CHUNK_BYTES;
-    if (nchunks < 1) nchunks = 1;
-    if (nchunks > KZG_MAX_CHUNKS) nchunks = KZG_MAX_CHUNKS;
-    if (nchunks > n) nchunks = n;
+    // The first sub-batch is half the target size (then the target) so that the first output starts
+    // crossing PCIe early; the target is large enough for a sub-batch to still fill the GPU.
+    // (KZG_CHUNK_MB / KZG_CHUNK_RAMP: tuning knobs read once from the environment.)
+    static const u64 chunk_bytes = [] { const char* e = getenv("KZG_CHUNK_MB"); const u64 v = e ? strtoull(e, nullptr, 10) : 0; return v ? v << 20 : KZG_CHUNK_BYTES; }();
+    static const u32 ramp_shift = [] { const char* e = getenv("KZG_CHUNK_RAMP"); return e ? (u32)strtoul(e, nullptr, 10) & 7u : 1u; }();
+    u64 nchunks = 0;
     u64 bounds[KZG_MAX_CHUNKS + 1];
-    {
-        u64 acc = 0, k = 0;
-        bounds[0] = 0;
-        for (u64 i = 0; i < n && k + 1 < nchunks; i++) {
-            acc += dst_cap[i];
-            if (acc * nchunks >= tot_dst * (k + 1)) bounds[++k] = i + 1;
+    bounds[0] = 0;
+    if (tot_dst <= chunk_bytes) { nchunks = 1; bounds[1] = n; }
+    else {
+        u64 acc = 0, goal = chunk_bytes >> ramp_shift, i = 0;
+        while (i < n) {
+            acc += dst_cap[i++];
+            if ((acc >= goal && nchunks + 1 < KZG_MAX_CHUNKS) || i == n) {
+                bounds[++nchunks] = i;
+                acc = 0;
+                if (goal < chunk_bytes) goal <<= 1;
+                else if (nchunks + 4 >= KZG_MAX_CHUNKS) goal <<= 1;      // very large calls: keep within the chunk limit
+            }
         }
-        while (k < nchunks) bounds[++k] = n;
     }
     cudaStream_t s_in = c->in_stream, s_cmp = c->own_stream, s_out = c->out_stream;
     c->last_stream = s_cmp;
