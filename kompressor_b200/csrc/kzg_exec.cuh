@@ -51,6 +51,10 @@ __device__ __forceinline__ void sts128(u32 a, uint4 v) {
 __device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
+// Predicated form: one instruction, no branch around it.
+__device__ __forceinline__ void cp_async16_if(bool p, u32 dst, const void* src) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" :: "r"(dst), "l"(src), "r"((u32)p) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 // History written earlier by this warp: read at L2 (the coherence point), never from a stale L1 line.
@@ -201,7 +205,7 @@ __device__ __forceinline__ bool stage_literals(u32 stage, const u8* lit, u32 l0,
     const u32 a = (u32)((uintptr_t)g0 & 15);
     const u32 nch = (a + (l1 - l0) + 15u) >> 4;             // <= 66
     g0 -= a;
-    if (lane < nch) cp_async16(stage + (lane << 4), g0 + (lane << 4));
+    cp_async16_if(lane < nch, stage + (lane << 4), g0 + (lane << 4));
     if (__builtin_expect(nch > 32, 0)) {
 #pragma unroll 1
         for (u32 c = lane + 32; c < nch; c += 32) cp_async16(stage + (c << 4), g0 + ((size_t)c << 4));
@@ -284,17 +288,17 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         // ---- matches whose source is not (entirely) inside the window any more but has been flushed: stage the
         // 16-byte chunks covering it now.  (Tv and F only grow, so the classification stays true.)
         const bool gsrc = !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
-        u32 gsa = 0;
-        if (gsrc) {
+        u32 gsa;
+        {
             const u8* g = out + spos;
             const u32 a = (u32)((uintptr_t)g & 15);
-            const u32 nch = (a + ml + 15u) >> 4;             // <= 5
+            const u32 nch = gsrc ? (a + ml + 15u) >> 4 : 0u;             // <= 5
             g -= a;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(mstage), "l"(g) : "memory");
-            if (nch > 1) asm volatile("cp.async.cg.shared.global [%0+16], [%1+16], 16;" :: "r"(mstage), "l"(g) : "memory");
-            if (nch > 2) asm volatile("cp.async.cg.shared.global [%0+32], [%1+32], 16;" :: "r"(mstage), "l"(g) : "memory");
-            if (nch > 3) asm volatile("cp.async.cg.shared.global [%0+48], [%1+48], 16;" :: "r"(mstage), "l"(g) : "memory");
-            if (nch > 4) asm volatile("cp.async.cg.shared.global [%0+64], [%1+64], 16;" :: "r"(mstage), "l"(g) : "memory");
+            cp_async16_if(nch > 0, mstage, g);
+            cp_async16_if(nch > 1, mstage + 16, g + 16);
+            cp_async16_if(nch > 2, mstage + 32, g + 32);
+            cp_async16_if(nch > 3, mstage + 48, g + 48);
+            cp_async16_if(nch > 4, mstage + 64, g + 64);
             gsa = mstage + a;
         }
         cp_commit();
