@@ -65,6 +65,10 @@ __device__ __forceinline__ void bar_arrive(u32 id) { asm volatile("bar.arrive %0
 __device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
+// Predicated form: one instruction, no branch around it.
+__device__ __forceinline__ void cp_async16_if(bool p, u32 dst, const void* src) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" :: "r"(dst), "l"(src), "r"((u32)p) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -305,9 +309,9 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
                     const i32 cP = P >> 7;
                     const i32 want = min(min(next_c - (cP - KZG_FSE_RING_CHUNKS), next_c + 1), 3);
                     const u8* gsrc = base + ((i64)next_c << 4);
-                    if (want > 0) cp_async16(s_ring + (((u32)next_c & 7u) << 4), gsrc);
-                    if (want > 1) cp_async16(s_ring + (((u32)(next_c - 1) & 7u) << 4), gsrc - 16);
-                    if (want > 2) cp_async16(s_ring + (((u32)(next_c - 2) & 7u) << 4), gsrc - 32);
+                    cp_async16_if(want > 0, s_ring + (((u32)next_c & 7u) << 4), gsrc);
+                    cp_async16_if(want > 1, s_ring + (((u32)(next_c - 1) & 7u) << 4), gsrc - 16);
+                    cp_async16_if(want > 2, s_ring + (((u32)(next_c - 2) & 7u) << 4), gsrc - 32);
                     next_c -= max(want, 0);
                     cp_commit();
                     pend2 = pend1;

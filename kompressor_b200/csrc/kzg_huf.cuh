@@ -29,6 +29,10 @@ __device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32
 __device__ __forceinline__ void cp_async16(u32 dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
+// Predicated form: one instruction, no branch around it.
+__device__ __forceinline__ void cp_async16_if(bool p, u32 dst, const void* src) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" :: "r"(dst), "l"(src), "r"((u32)p) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -120,11 +124,11 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
             cp_wait<1>();                                                                                 \
             ready_lo = pend2;                                                                             \
             const i32 cP_ = P >> 7;                                                                       \
-            _Pragma("unroll") for (int r_ = 0; r_ < 2; r_++)                                              \
-                if (next_c >= 0 && next_c > cP_ - 8) {                                                    \
-                    cp_async16(s_ring + (((u32)next_c & 7u) << 4), base + ((size_t)next_c << 4));         \
-                    next_c--;                                                                             \
-                }                                                                                         \
+            const i32 want_ = min(min(next_c - (cP_ - 8), next_c + 1), 2);                                \
+            const u8* g_ = base + ((i64)next_c << 4);                                                     \
+            cp_async16_if(want_ > 0, s_ring + (((u32)next_c & 7u) << 4), g_);                             \
+            cp_async16_if(want_ > 1, s_ring + (((u32)(next_c - 1) & 7u) << 4), g_ - 16);                  \
+            next_c -= max(want_, 0);                                                                      \
             cp_commit();                                                                                  \
             pend2 = pend1;                                                                                \
             pend1 = next_c + 1;                                                                           \
