@@ -97,7 +97,9 @@ typedef struct {
 } kzg_batch_stats;
 int kzg_last_batch_stats(kzg_ctx* ctx, kzg_batch_stats* out);
 
-/* Raw-content dictionary used as history prefix by the following batches (NULL clears it).
+/* Dictionary used by the following batches (NULL clears it): a raw-content dictionary is a history prefix;
+ * a formatted one (magic 0xEC30A437) also preloads every frame's Huffman / FSE tables and repeat offsets and
+ * carries a dictionary ID that frames naming another ID are rejected against (dictionary_wrong, 32).
  * Replaces ZSTD_DCtx_loadDictionary (Wrapper.cpp:58-73) on the batch layer. */
 int kzg_ctx_set_dictionary(kzg_ctx* ctx, const void* dict, size_t size);
 

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <vector>
 #include <new>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -31,6 +32,10 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Device constants: predefined FSE distributions, packed LL/ML code tables, and the entropy tables of the
+// formatted dictionary currently loaded (if any).
+struct KzgConsts { KzgFseDesc def; u32 codes[96]; KzgFseDesc dict_fse; KzgHufDesc dict_huf; };
+
 struct kzg_ctx {
     int device = 0;
     int sm_count = 0;
@@ -50,9 +55,11 @@ struct kzg_ctx {
     // staging for the host-pointer form
     DevBuf st_src, st_dst, st_tab;
     // raw-content dictionary applied to every frame of subsequent batches
-    DevBuf dict;
+    DevBuf dict;                   // dictionary content (history prefix)
     u32 dict_size = 0;
-    std::vector<u8> dict_host;
+    std::vector<u8> dict_host;     // the bytes last loaded (to skip reloading the same dictionary)
+    // formatted dictionary (magic 0xEC30A437): entropy tables live behind the constants, see KzgConsts
+    u32 dict_id = 0, dict_entropy = 0, dict_rep[3] = { 1, 4, 8 };
     // optional per-stage CUDA events (kzg_ctx_set_profiling)
     bool profiling = false;
     cudaEvent_t ev[KZG_N_STAGES + 1] = {};
@@ -133,9 +140,9 @@ extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
              cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); kzg_ctx_destroy(c); return (int)KZG_E_MEMORY; }
     // constants: default FSE descriptor + packed code tables
-    struct { KzgFseDesc d; u32 codes[96]; } hc;
+    static KzgConsts hc;
     memset(&hc, 0, sizeof hc);
-    kzg_default_fse_desc(hc.d);
+    kzg_default_fse_desc(hc.def);
     kzg_code_tables(hc.codes, hc.codes + 36);
     if (c->consts.ensure(sizeof hc) || c->ctr.ensure(sizeof(KzgCounters)) ||
         cudaMemcpy(c->consts.p, &hc, sizeof hc, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -162,21 +169,56 @@ extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     delete c;
 }
 
-// Sets (dict != NULL) or clears the raw-content dictionary used as history prefix by the following
-// batches (reference: ZSTD_DCtx_loadDictionary at Wrapper.cpp:58-73). Formatted dictionaries
-// (magic 0xEC30A437: entropy tables + repeat offsets) are not supported yet -> parameter_unsupported.
+// Sets (dict != NULL) or clears the dictionary used by the following batches (reference:
+// ZSTD_DCtx_loadDictionary at Wrapper.cpp:58-73).  A raw-content dictionary is a history prefix.  A formatted
+// dictionary (magic 0xEC30A437: dictID, Huffman table, OF / ML / LL FSE tables, three repeat offsets, content;
+// libzstd ZSTD_loadDEntropy order) also preloads every frame's entropy tables and repeat offsets.
 extern "C" int kzg_ctx_set_dictionary(kzg_ctx* c, const void* dict, size_t size) {
     if (!c) return -(int)KZG_E_GENERIC;
     std::lock_guard<std::mutex> lock(c->mu);
-    if (!dict || size == 0) { c->dict_size = 0; c->dict_host.clear(); return 0; }
-    if (size >= 8 && kzg_rd32((const u8*)dict) == KZG_DICT_MAGIC) return -40;
+    if (!dict || size == 0) { c->dict_size = 0; c->dict_host.clear(); c->dict_id = 0; c->dict_entropy = 0; return 0; }
     if (size > 0x7FFFFFFFu) return -(int)KZG_E_MEMORY;
     if (c->dict_host.size() == size && memcmp(c->dict_host.data(), dict, size) == 0) return 0;
     CK(cudaSetDevice(c->device));
-    if (c->dict.ensure(size + 16)) return -(int)KZG_E_MEMORY;
-    CK(cudaMemcpy(c->dict.p, dict, size, cudaMemcpyHostToDevice));
+    const u8* p = (const u8*)dict;
+    const u8* const end = p + size;
+    u32 id = 0, entropy = 0, rep[3] = { 1, 4, 8 };
+    if (size >= 8 && kzg_rd32(p) == KZG_DICT_MAGIC) {
+        static KzgFseDesc fd;
+        static KzgHufDesc hd;
+        memset(&fd, 0, sizeof fd);
+        memset(&hd, 0, sizeof hd);
+        id = kzg_rd32(p + 4);
+        p += 8;
+        const u32 hsz = kzg_read_huf_weights(p, (u32)(end - p), hd.weight, hd.nsym, hd.maxbits);
+        if (hsz == 0) return -(int)KZG_E_DICT_CORRUPTED;
+        p += hsz;
+        const u32 order[3] = { 1, 2, 0 }, max_sym[3] = { 35, 31, 52 }, max_log[3] = { 9, 8, 9 };   // stored as OF, ML, LL
+        for (u32 k = 0; k < 3; k++) {
+            const u32 t = order[k];
+            u32 nsym = 0, log = 0;
+            const u32 h = kzg_read_ncount(p, (u32)(end - p), max_sym[t], max_log[t], fd.norm[t], nsym, log);
+            if (h == 0) return -(int)KZG_E_DICT_CORRUPTED;
+            fd.kind[t] = 2; fd.log[t] = (u8)log; fd.nsym[t] = (u8)nsym;
+            p += h;
+        }
+        if (p + 12 > end) return -(int)KZG_E_DICT_CORRUPTED;
+        for (u32 k = 0; k < 3; k++) {
+            rep[k] = kzg_rd32(p + 4 * k);
+            if (rep[k] == 0 || rep[k] > (u64)(end - (p + 12))) return -(int)KZG_E_DICT_CORRUPTED;
+        }
+        p += 12;
+        entropy = 1;
+        CK(cudaMemcpy((u8*)c->consts.p + offsetof(KzgConsts, dict_fse), &fd, sizeof fd, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy((u8*)c->consts.p + offsetof(KzgConsts, dict_huf), &hd, sizeof hd, cudaMemcpyHostToDevice));
+    }
+    const size_t content = (size_t)(end - p);
+    if (c->dict.ensure(content + 16)) return -(int)KZG_E_MEMORY;
+    if (content) CK(cudaMemcpy(c->dict.p, p, content, cudaMemcpyHostToDevice));
     c->dict_host.assign((const u8*)dict, (const u8*)dict + size);
-    c->dict_size = (u32)size;
+    c->dict_size = (u32)content;
+    c->dict_id = id; c->dict_entropy = entropy;
+    c->dict_rep[0] = rep[0]; c->dict_rep[1] = rep[1]; c->dict_rep[2] = rep[2];
     return 0;
 }
 
@@ -281,11 +323,15 @@ static int enqueue_batch(kzg_ctx* c, const void* d_src, const uint64_t* d_src_of
     b.hlist = (u32*)c->hlist.p; b.slist = (u32*)c->slist.p;
     b.lit_pool = (u8*)c->lit.p; b.seq_pool = (u64*)c->seq.p; b.fse_tab = (u16*)c->fsetab.p;
     b.ctr = (KzgCounters*)c->ctr.p;
-    b.fse_default = (const KzgFseDesc*)c->consts.p;
-    b.code_tables = (const u32*)((const u8*)c->consts.p + sizeof(KzgFseDesc));
+    b.fse_default = (const KzgFseDesc*)((const u8*)c->consts.p + offsetof(KzgConsts, def));
+    b.code_tables = (const u32*)((const u8*)c->consts.p + offsetof(KzgConsts, codes));
+    b.fse_dict = (const KzgFseDesc*)((const u8*)c->consts.p + offsetof(KzgConsts, dict_fse));
+    b.huf_dict = (const KzgHufDesc*)((const u8*)c->consts.p + offsetof(KzgConsts, dict_huf));
     b.lit_cap = c->lit_cap; b.seq_cap = c->seq_cap;
     b.block_cap = (u32)c->block_cap; b.cblock_cap = (u32)c->cblock_cap;
-    b.dict = (const u8*)c->dict.p; b.dict_size = c->dict_size; b.dict_id = 0;
+    b.dict = (const u8*)c->dict.p; b.dict_size = c->dict_size; b.dict_id = c->dict_id;
+    b.dict_entropy = c->dict_entropy;
+    b.dict_rep[0] = c->dict_rep[0]; b.dict_rep[1] = c->dict_rep[1]; b.dict_rep[2] = c->dict_rep[2];
     CK(cudaMemsetAsync(c->ctr.p, 0, sizeof(KzgCounters), stream));
     const int launches = kzg_launch_batch(b, c->sm_count, stream, c->profiling ? c->ev : nullptr);
     c->ev_valid = c->profiling;

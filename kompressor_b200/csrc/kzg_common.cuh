@@ -141,6 +141,7 @@ struct KzgCounters {
 };
 
 #define KZG_INVALID_OWNER 0xFFFFFFFEu
+#define KZG_DICT_OWNER 0xFFFFFFFDu      // table comes from the formatted dictionary loaded into the context
 
 struct KzgBatch {
     // caller's frame table (device pointers)
@@ -170,10 +171,15 @@ struct KzgBatch {
     const u32* code_tables;   // 36 LL + 53 ML packed (extra_bits << 24 | baseline)
     u64 lit_cap, seq_cap;
     u32 block_cap, cblock_cap;
-    // optional raw-content dictionary prefix shared by all frames of the batch
+    // optional dictionary shared by all frames of the batch: `dict` is its content (history prefix); a
+    // formatted dictionary (magic 0xEC30A437) also brings entropy tables and repeat offsets
     const u8* dict;
     u32 dict_size;
     u32 dict_id;
+    u32 dict_entropy;           // 1 if fse_dict / huf_dict / dict_rep are valid
+    u32 dict_rep[3];
+    const KzgFseDesc* fse_dict;
+    const KzgHufDesc* huf_dict;
 };
 
 

@@ -210,9 +210,9 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
         // post warp ML.  Idle lanes get one-cell tables so the straight-line loop stays in bounds.
         if (j.nseq) {
             const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-            const KzgFseDesc* d0 = o0 == KZG_NONE ? B.fse_default : &B.fse[o0];
-            const KzgFseDesc* d1 = o1 == KZG_NONE ? B.fse_default : &B.fse[o1];
-            const KzgFseDesc* d2 = o2 == KZG_NONE ? B.fse_default : &B.fse[o2];
+            const KzgFseDesc* d0 = kzg_fse_desc_of(B, o0);
+            const KzgFseDesc* d1 = kzg_fse_desc_of(B, o1);
+            const KzgFseDesc* d2 = kzg_fse_desc_of(B, o2);
             j.logLL = d0->kind[0] == 1 ? 0u : (u32)d0->log[0];
             j.logOF = d1->kind[1] == 1 ? 0u : (u32)d1->log[1];
             j.logML = d2->kind[2] == 1 ? 0u : (u32)d2->log[2];
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
             j.block_max = B.frames[cb->frame].block_max;
             j.out = B.seq_pool + cb->seq_out;
             if (!cb->first_in_frame) { j.rep0 = KZG_OFF_SYM | 0; j.rep1 = KZG_OFF_SYM | 1; j.rep2 = KZG_OFF_SYM | 2; }
+            else if (B.dict_entropy) { j.rep0 = B.dict_rep[0]; j.rep1 = B.dict_rep[1]; j.rep2 = B.dict_rep[2]; }
         } else if (chain) { sts16(tLL, 1u << 6); sts16(tOF, 1u << 6); sts16(tML, 1u << 6); }
         Result res;
         res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;

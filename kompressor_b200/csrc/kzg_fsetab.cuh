@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(KZG_TAB_WARPS * 32) kzg_fsetab_kernel(KzgBatch
         if (cb->status_seq != KZG_OK || cb->status_lit != KZG_OK) continue;
         u16* out = B.fse_tab + (size_t)si * KZG_TAB_CELLS;
         const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-        build(sc, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0, out, lane);
+        build(sc, kzg_fse_desc_of(B, o0), 0, out, lane);
         __syncwarp();
-        build(sc, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2, out + 512, lane);
+        build(sc, kzg_fse_desc_of(B, o2), 2, out + 512, lane);
         __syncwarp();
-        build(sc, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1, out + 1024, lane);
+        build(sc, kzg_fse_desc_of(B, o1), 1, out + 1024, lane);
         __syncwarp();
     }
 }

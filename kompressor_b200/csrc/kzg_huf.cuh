@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
         // ---- table: built by the block's four lanes (the rings serve as scratch until the streams start)
         u32 maxbits = KZG_HUF_MAXBITS, nsym = 0;
         if (valid) {
-            const KzgHufDesc* hd = &B.huf[cb->huf_owner];
+            const KzgHufDesc* hd = kzg_huf_desc_of(B, cb->huf_owner);
             maxbits = hd->maxbits; nsym = hd->nsym;
             kzg_huf_build_phase1(sc, hd->weight, nsym, st);
         }

@@ -18,6 +18,15 @@ static inline u32 kzg_host_or32(u32* p, u32 v) { const u32 o = *p; *p |= v; retu
 #define KZG_ATOMIC_OR32(p, v) kzg_host_or32((p), (v))
 #endif
 
+// Entropy description a table owner stands for: a compressed block of the batch, the predefined
+// distributions (KZG_NONE) or the formatted dictionary (KZG_DICT_OWNER).
+KZG_HD const KzgFseDesc* kzg_fse_desc_of(const KzgBatch& B, u32 owner) {
+    return owner == KZG_NONE ? B.fse_default : (owner == KZG_DICT_OWNER ? B.fse_dict : &B.fse[owner]);
+}
+KZG_HD const KzgHufDesc* kzg_huf_desc_of(const KzgBatch& B, u32 owner) {
+    return owner == KZG_DICT_OWNER ? B.huf_dict : &B.huf[owner];
+}
+
 // scan: frame header + block-header walk of frame i -> KzgFrame, KzgBlock[], KzgCBlock[] stubs (stage s1)
 KZG_HD void kzg_stage_scan(const KzgBatch& B, u32 i) {
     const u8* f = B.src + B.src_off[i];
@@ -117,7 +126,9 @@ KZG_HD void kzg_stage_parse(const KzgBatch& B, u32 c) {
 KZG_HD void kzg_stage_link(const KzgBatch& B, u32 i) {
     const KzgFrame fr = B.frames[i];
     if (fr.status != KZG_OK) return;
-    u32 huf_cur = KZG_INVALID_OWNER, fse_cur[3] = { KZG_INVALID_OWNER, KZG_INVALID_OWNER, KZG_INVALID_OWNER };
+    // a formatted dictionary preloads the Huffman table and the three FSE tables of every frame
+    const u32 start = B.dict_entropy ? KZG_DICT_OWNER : KZG_INVALID_OWNER;
+    u32 huf_cur = start, fse_cur[3] = { start, start, start };
     u32 seen_seq = 0;
     for (u32 k = 0; k < fr.n_blocks; k++) {
         const u32 c = B.blocks[fr.first_block + k].cidx;
@@ -170,10 +181,11 @@ KZG_HD void kzg_stage_fse_block(const KzgBatch& B, KzgCBlock* cb, u16* tLL, u16*
                                 const u32* llx, const u32* mlx) {
     if (cb->status_seq != KZG_OK || cb->status_lit != KZG_OK) return;
     const u32 o0 = cb->fse_owner[0], o1 = cb->fse_owner[1], o2 = cb->fse_owner[2];
-    const u32 logML = kzg_fse_build_desc(tML, o2 == KZG_NONE ? B.fse_default : &B.fse[o2], 2, tLL);
-    const u32 logOF = kzg_fse_build_desc(tOF, o1 == KZG_NONE ? B.fse_default : &B.fse[o1], 1, tLL);
-    const u32 logLL = kzg_fse_build_desc(tLL, o0 == KZG_NONE ? B.fse_default : &B.fse[o0], 0, scrLL);
+    const u32 logML = kzg_fse_build_desc(tML, kzg_fse_desc_of(B, o2), 2, tLL);
+    const u32 logOF = kzg_fse_build_desc(tOF, kzg_fse_desc_of(B, o1), 1, tLL);
+    const u32 logLL = kzg_fse_build_desc(tLL, kzg_fse_desc_of(B, o0), 0, scrLL);
     u32 r0 = 1, r1 = 4, r2 = 8;
+    if (B.dict_entropy) { r0 = B.dict_rep[0]; r1 = B.dict_rep[1]; r2 = B.dict_rep[2]; }
     if (!cb->first_in_frame) { r0 = KZG_OFF_SYM | 0; r1 = KZG_OFF_SYM | 1; r2 = KZG_OFF_SYM | 2; }
     KzgSeqOut res;
     kzg_decode_sequences(B.src + cb->src + cb->seq_src, cb->seq_size, cb->n_seq, tLL, logLL, tOF, logOF, tML, logML,
@@ -200,6 +212,7 @@ KZG_HD void kzg_stage_offsets(const KzgBatch& B, u32 i) {
     u64 pos = 0;
     u32 err = KZG_OK;
     u32 rep[3] = { 1, 4, 8 };
+    if (B.dict_entropy) { rep[0] = B.dict_rep[0]; rep[1] = B.dict_rep[1]; rep[2] = B.dict_rep[2]; }
     for (u32 k = 0; k < fr->n_blocks; k++) {
         KzgBlock* blk = &B.blocks[fr->first_block + k];
         if (blk->type == 2) {

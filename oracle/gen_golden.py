@@ -69,6 +69,12 @@ def main() -> None:
     add("mixed_400k_l19_streamed", z.compress(mixed, 19, checksum=True, pledged=False), mixed,
         "multi-block, treeless literals, repeat-mode tables, cross-block matches", keep_raw=False)
     add("mixed_400k_l3", z.compress(mixed, 3), mixed, "4 blocks at level 3", keep_raw=False)
+    # formatted dictionary (ZDICT_trainFromBuffer): entropy tables + repeat offsets + content, dictID in the frame
+    fdict = z.train_dictionary([bytes(corpus.generate("json", 100 + i, 2000)) for i in range(200)], 4096)
+    assert fdict[:4] == bytes.fromhex("37a430ec")
+    djson = bytes(corpus.generate("json", 999, 3000))
+    add("dict_formatted_json_3k", z.compress(djson, 3, dictionary=fdict), djson,
+        "formatted dictionary: treeless literals / repeat-mode tables / repeat offsets come from the dictionary", dictionary=fdict)
     # hand-made: pure RLE block frame and skippable + frame
     rle = bytes.fromhex("28b52ffd") + bytes([0x20, 100]) + struct.pack("<I", (100 << 3) | (1 << 1) | 1)[:3] + b"Z"
     add("rle_block_100", rle, b"Z" * 100, "single RLE block (hand-made)")

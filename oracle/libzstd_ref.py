@@ -121,7 +121,23 @@ class LibZstd:
         L.ZSTD_compress2.restype = c_size_t
         L.ZSTD_compressBound.argtypes = [c_size_t]
         L.ZSTD_compressBound.restype = c_size_t
+        if hasattr(L, "ZDICT_trainFromBuffer"):
+            L.ZDICT_trainFromBuffer.argtypes = [c_void_p, c_size_t, c_void_p, POINTER(c_size_t), c_uint]
+            L.ZDICT_trainFromBuffer.restype = c_size_t
         self.version = L.ZSTD_versionString().decode()
+
+    # ------------------------------------------------------------------ dictionaries
+    def train_dictionary(self, samples: list[bytes], capacity: int = 4096) -> bytes:
+        """ZDICT_trainFromBuffer: a *formatted* dictionary (magic 0xEC30A437: dictID, entropy tables, repeat
+        offsets, content) trained on `samples`."""
+        import ctypes
+        blob = b"".join(samples)
+        sizes = (c_size_t * len(samples))(*[len(x) for x in samples])
+        out = ctypes.create_string_buffer(capacity)
+        n = self.lib.ZDICT_trainFromBuffer(out, capacity, blob, sizes, len(samples))
+        if self.is_error(n):
+            raise RuntimeError("ZDICT_trainFromBuffer: " + self.error_name(n))
+        return out.raw[:n]
 
     # ------------------------------------------------------------------ errors
     def is_error(self, code: int) -> bool:

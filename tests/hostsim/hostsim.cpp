@@ -74,7 +74,7 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     for (u32 h = 0; h < ctr.n_hblocks; h++) {
         KzgCBlock* cb = &cblocks[hlist[h]];
         if (cb->status_lit != KZG_OK || cb->huf_owner == KZG_INVALID_OWNER) continue;
-        const KzgHufDesc* hd = &huf[cb->huf_owner];
+        const KzgHufDesc* hd = kzg_huf_desc_of(B, cb->huf_owner);
         alignas(16) KzgHufScratch sc;
         for (u32 st = 0; st < 4; st++) kzg_huf_build_phase1(&sc, hd->weight, hd->nsym, st);
         for (u32 st = 0; st < 4; st++) kzg_huf_build_phase2(&sc, hd->maxbits, st);

@@ -117,6 +117,38 @@ def test_far_offsets_and_wide_sequences(dec, libzstd):
         assert hashlib.sha256(o).digest() == hashlib.sha256(raw).digest()
 
 
+def test_formatted_dictionary_batch(dec, oracle_mod, libzstd, manifest):
+    """Formatted dictionary (ZDICT-trained: entropy tables, repeat offsets, content, dictID) on the batch layer:
+    the golden vector, frames of several sizes incl. multi-block ones, the wrong dictionary, no dictionary."""
+    import base64
+    import corpus
+    from helpers import gbytes as gb
+    v = next(x for x in manifest["vectors"] if x["name"] == "dict_formatted_json_3k")
+    fdict = base64.b64decode(v["dictionary_b64"])
+    raws = [bytes(corpus.generate("json", 500 + i, n)) for i, n in enumerate((0, 1, 40, 700, 3000, 70000, 300000))]
+    frames = [gb(v["name"] + ".zst")] + [libzstd.compress(r, lvl, dictionary=fdict, checksum=True) for r in raws for lvl in (1, 3, 19)]
+    expect = [gb(v["name"] + ".raw")] + [r for r in raws for _ in range(3)]
+    try:
+        dec.set_dictionary(fdict)
+        outs, status, _ = run(dec, frames, [len(r) + 8 for r in expect])
+        assert (status == 0).all(), status
+        assert outs == expect
+        for f, e in list(zip(frames, expect))[::5]:
+            o, err = oracle_mod.decompress(f, len(e) + 8, fdict)
+            assert err == 0 and o == e
+        # a dictionary with another ID: frames name their dictID -> dictionary_wrong (32), as libzstd
+        other = bytearray(fdict); other[4] ^= 0x5A
+        dec.set_dictionary(bytes(other))
+        _, status, _ = run(dec, frames[:4], [len(r) + 8 for r in expect[:4]])
+        assert (status == 32).all(), status
+        _, lerr = libzstd.decompress_oneshot(frames[0], 65536, dictionary=bytes(other))
+        assert lerr == 32
+    finally:
+        dec.set_dictionary(None)
+    _, status, _ = run(dec, frames[:4], [len(r) + 8 for r in expect[:4]])
+    assert (status != 0).all()
+
+
 def test_unaligned_output_offsets(dec, libzstd):
     import corpus
     raws = [bytes(corpus.generate("logs", 90 + i, 30000 + 17 * i)) for i in range(9)]

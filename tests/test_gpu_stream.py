@@ -63,6 +63,18 @@ def test_dictionaryRoundtrip(api, libzstd):             # ZstdTest.kt:49-65
     assert len(compressed) < len(compress_like_kompressor(libzstd, data))
 
 
+def test_formattedDictionaryRoundtrip(api, libzstd):    # same constructor signature, ZDICT-trained dictionary
+    import corpus
+    core, io, zstd = api
+    dictionary = libzstd.train_dictionary([bytes(corpus.generate("logs", 300 + i, 1500)) for i in range(200)], 8192)
+    data = bytes(corpus.generate("logs", 777, 50000))
+    compressed = compress_like_kompressor(libzstd, data, dictionary=dictionary)
+    assert core.transform(zstd.ZstdDecompressor(dictionary=dictionary), compressed) == data
+    assert io.pipe(compressed, zstd.ZstdDecompressor(dictionary=dictionary)).readByteArray() == data
+    with pytest.raises(zstd.IllegalStateException):     # must fail without the dictionary
+        core.transform(zstd.ZstdDecompressor(), compressed)
+
+
 def test_sampleHello(api):                              # ZstdTest.kt:84-91
     core, _, zstd = api
     compressed = base64.b64decode("KLUv/QRYuQAAaGVsbG8gY29tcHJlc3Npb24gd29ybGR8Qm9f")
