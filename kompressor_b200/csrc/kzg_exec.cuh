@@ -283,7 +283,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
         const i32 be = (i32)((u32)(carry >> 46));
         // make room for the whole batch first if it fits a window (the usual case), so that the source
         // classification below sees the window it will run with
-        if (__builtin_expect(longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE, 0)) slide(w, cur, lane);
+        if (__builtin_expect(longm == 0 && (u32)(be - w.T0) > KZG_EX_TILE, 0)) { flush(w, cur, false, lane); slide(w, cur, lane); }
 
         // ---- matches whose source is not (entirely) inside the window any more but has been flushed: stage the
         // 16-byte chunks covering it now.  (Tv and F only grow, so the classification stays true.)
@@ -347,7 +347,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 __syncwarp();
             }
             cur = ge;
-            flush(w, cur, false, lane);
+            if ((b0 & 96u) == 96u) flush(w, cur, false, lane);   // every fourth batch: ~2 KiB per flush
         };
 
         if (__builtin_expect(longm == 0 && (u32)(be - cur) <= KZG_EX_CAP, 1)) {
@@ -369,7 +369,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 if (grp) {
                     const u32 lastl = 31 - __clz(grp);
                     const i32 ge = (i32)__shfl_sync(0xFFFFFFFFu, out_end, lastl);
-                    if ((u32)(ge - w.T0) > KZG_EX_TILE) slide(w, cur, lane);
+                    if ((u32)(ge - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); }
                     run_group((grp >> lane) & 1u, ge);
                     todo &= ~grp;
                 } else {
