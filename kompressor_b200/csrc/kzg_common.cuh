@@ -41,6 +41,8 @@ enum : u32 {
 };
 
 #define KZG_BLOCK_MAX (128u * 1024u)
+#define KZG_BULK_MIN 256u            // literal runs of at least this many bytes are copied by the bulk kernel ...
+#define KZG_BULK_SUM 4096u           // ... in blocks whose long runs add up to at least this much (else not worth a record scan)
 #define KZG_HUF_MAXBITS 11
 #define KZG_MAGIC 0xFD2FB528u
 #define KZG_SKIP_MAGIC 0x184D2A50u
@@ -115,6 +117,7 @@ struct KzgCBlock {          // one per compressed block
     u32 rep_init[3];        // concrete repeat offsets at block start (filled by the frame-order pass)
     u32 rep_final[3];       // encoded (possibly symbolic) repeat offsets after the block
     u32 first_in_frame;     // 1 if no compressed block with sequences precedes it in its frame
+    u32 bulk_lits;          // 1 if the literal runs of >= KZG_BULK_MIN bytes add up to >= KZG_BULK_SUM: the bulk kernel copies them
 };
 
 struct KzgFseDesc {         // entropy description parsed from a compressed block
@@ -137,7 +140,9 @@ struct KzgCounters {
     u64 lit_used, seq_used;
     u32 overflow;           // bit0 blocks, bit1 cblocks, bit2 literal pool, bit3 sequence pool
     u32 ticket_huf, ticket_fse, ticket_exec, ticket_raw;
-    u32 pad[3];
+    u32 n_bulk;             // entries of blist
+    u32 n_defer;            // entries of dlist
+    u32 ticket_exec2;
 };
 
 #define KZG_INVALID_OWNER 0xFFFFFFFEu
@@ -163,6 +168,8 @@ struct KzgBatch {
     KzgHufDesc* huf;
     u32* hlist;         // compressed blocks with Huffman-coded literals
     u32* slist;         // compressed blocks with sequences
+    u32* blist;         // blocks with work for the bulk kernel (filled by the offsets stage)
+    u32* dlist;         // frames the hot execute kernel left to the full one (long runs)
     u8* lit_pool;
     u64* seq_pool;
     u16* fse_tab;       // built FSE decode tables, 1280 cells (LL 512 | ML 512 | OF 256) per entry of slist

@@ -170,7 +170,7 @@ KZG_HD u32 kzg_rep_dec(u32 r) {          // "rep0 - 1"
     return r - 1;
 }
 
-struct KzgSeqOut { u32 status, regen, lit_used, rep0, rep1, rep2; };
+struct KzgSeqOut { u32 status, regen, lit_used, rep0, rep1, rep2, bulk_lits; };
 
 // ZSTD_decodeSequence loop for one block (Appendix A.6): the sequential state machine.
 //  bits/size: sequence bitstream; tLL/tOF/tML: decode tables; llx/mlx: packed code tables;
@@ -180,7 +180,7 @@ KZG_HD void kzg_decode_sequences(const u8* bits, u32 size, u32 nseq,
                                  const u32* llx, const u32* mlx, u32 rep0, u32 rep1, u32 rep2,
                                  u32 lit_regen, u32 block_max, u64* out, KzgSeqOut& res) {
     KzgBwdQ b;
-    res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;
+    res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0; res.bulk_lits = 0;
     res.rep0 = rep0; res.rep1 = rep1; res.rep2 = rep2;
     if (!b.init(bits, size)) return;
     b.ensure32();
@@ -214,6 +214,7 @@ KZG_HD void kzg_decode_sequences(const u8* bits, u32 size, u32 nseq,
         }
         lit_end += ll;
         out_end += ll + ml;
+        if (ll >= KZG_BULK_MIN) res.bulk_lits += ll;          // sum of long runs; turned into the flag by the caller
         if (lit_end > lit_regen || out_end > block_max) return;
         out[i] = kzg_pack_seq(off, lit_end, out_end);
         if (i + 1 < nseq) {

@@ -215,14 +215,16 @@ __device__ __forceinline__ bool stage_literals(u32 stage, const u8* lit, u32 l0,
 
 }  // namespace kzg_ex
 
-// Executes one compressed block with sequences. Returns true (uniformly) if the block is corrupt.
-// smem: this warp's shared memory (window | literal staging | match staging).
-__device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const KzgCBlock* cb, u8* out,
+// Executes one compressed block with sequences. Returns (uniformly) 0 = done, 1 = the block is corrupt, 2 = the
+// block needs the FULL variant.  smem: this warp's shared memory (window | literal staging | match staging).
+template <bool FULL>
+__device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBlock& blk, const KzgCBlock* cb, u8* out,
                                                    u32 smem, u32 lane) {
     using namespace kzg_ex;
     const u32 nseq = cb->n_seq, lit_regen = cb->lit_regen, lit_type = cb->lit_type;
     const u8* lit = lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
     const bool lfill = lit_type == 1;
+    const bool bulk_lits = cb->bulk_lits != 0;      // long literal runs of this block were copied by kzg_bulk_kernel
     const u32 rle = lfill ? (u32)lit[0] : 0u;
     const u32 lit_align = (u32)((uintptr_t)lit & 15);
     const u64* seqs = B.seq_pool + cb->seq_out;
@@ -238,7 +240,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     w.Tv = 0; w.F = 0;
     w.boff = (i64)blk.out_off;
     w.dict_end = B.dict + B.dict_size;
-    bool err = false;
+    bool err = false, defer = false;
     u64 carry = 0;                       // last record of the previous batch
     u64 rec_next = lane < nseq ? seqs[lane] : 0ull;
     const u64* rec_ptr = seqs + lane;
@@ -377,10 +379,12 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                     const u32 l_ll = __shfl_sync(0xFFFFFFFFu, ll, stop), l_ml = __shfl_sync(0xFFFFFFFFu, ml, stop);
                     const u32 l_ple = __shfl_sync(0xFFFFFFFFu, p_lit_end, stop), l_poe = __shfl_sync(0xFFFFFFFFu, p_out_end, stop);
                     const u32 l_off = __shfl_sync(0xFFFFFFFFu, off, stop);
+                    if (!FULL && l_off < l_ml && l_ml >= 1024u) { defer = true; break; }      // a long run: left to the FULL variant
                     flush(w, cur, true, lane);
                     __syncwarp();
                     u8* d = out + l_poe;
-                    if (lfill) warp_set_global(d, rle, l_ll, lane);
+                    if (bulk_lits && l_ll >= KZG_BULK_MIN) { /* written by kzg_bulk_kernel */ }
+                    else if (lfill) warp_set_global(d, rle, l_ll, lane);
                     else warp_copy_global<false>(d, lit + l_ple, l_ll, lane);
                     __threadfence_block();
                     __syncwarp();
@@ -388,8 +392,42 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                     const i32 sp = (i32)(l_poe + l_ll) - (i32)l_off;
                     if (l_off >= l_ml && w.boff + sp >= 0) {
                         warp_copy_global<true>(d, out + sp, l_ml, lane);      // disjoint source inside the frame
+                    } else if (FULL && l_ml >= 1024u && w.boff + sp >= 0 && l_off >= 64) {
+                        // overlapping with a long period: pieces of l_off bytes, each disjoint from its (already
+                        // written) source
+                        for (u32 done = 0; done < l_ml; done += l_off) {
+                            warp_copy_global<true>(d + done, out + sp + done, min(l_off, l_ml - done), lane);
+                            __threadfence_block();
+                            __syncwarp();
+                        }
+                    } else if (FULL && l_ml >= 1024u && w.boff + sp >= 0) {
+                        // overlapping with a short period (runs): expand the period to ~1 KiB in the (flushed, hence free)
+                        // window, then stream it out as 16-byte vectors; positions wrap by compare-subtract, no division
+                        const u32 L = l_off * (1024u / l_off);
+                        for (u32 k = lane; k < L; k += 32) sts8(w.tile + k, ldg8_hist(out + sp + (i32)(k % l_off)));
+                        __syncwarp();
+                        const u32 head = min(l_ml, (u32)((16 - ((uintptr_t)d & 15)) & 15));
+                        if (lane < head) d[lane] = (u8)lds8(w.tile + lane);                 // head < 16 <= L
+                        const u32 nvec = (l_ml - head) >> 4;
+                        u32 p = (head + (lane << 4)) % L;                                   // pattern phase of this lane's chunk
+                        const u32 stepw = 512u % L;                                         // phase advance per pass of 32 chunks
+                        for (u32 v = lane; v < nvec; v += 32) {
+                            u32 wv[4];
+                            u32 q = p;
+#pragma unroll
+                            for (int wi = 0; wi < 4; wi++) {
+                                u32 x = 0;
+#pragma unroll
+                                for (int bi = 0; bi < 4; bi++) { x |= lds8(w.tile + q) << (8 * bi); q++; q = q >= L ? q - L : q; }
+                                wv[wi] = x;
+                            }
+                            reinterpret_cast<uint4*>(d + head)[v] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                            p += stepw; p = p >= L ? p - L : p;
+                        }
+                        const u32 donev = head + (nvec << 4);
+                        if (lane < l_ml - donev) d[donev + lane] = (u8)lds8(w.tile + (donev + lane) % L);
                     } else {
-                        // overlapping (period l_off) or reaching into the dictionary: every byte equals one of the
+                        // a short overlapping match, or one reaching into the dictionary: every byte equals one of the
                         // l_off bytes just before the match, all of which are final
                         for (u32 k = lane; k < l_ml; k += 32) {
                             const i32 p = sp + (i32)(l_off >= l_ml ? k : k % l_off);
@@ -406,6 +444,7 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
                 }
             }
         }
+        if (defer) break;
         // ---- stage the next batch's literals (this batch no longer reads the staging area)
         cp_wait<0>();
         __syncwarp();
@@ -420,22 +459,27 @@ __device__ __forceinline__ bool kzg_exec_sequences(const KzgBatch& B, const KzgB
     }
     cp_wait<0>();
     __syncwarp();
-    if (err) return true;
+    if (err) return 1u;
+    if (defer) return 2u;
     // tail: what is left in the window, then the literals after the last sequence
     flush(w, cur, true, lane);
     __syncwarp();
     {
         const u32 used = (u32)(carry >> 28) & 0x3FFFFu;
-        if (lit_regen > used) {
+        if (lit_regen > used && lit_regen - used < KZG_BULK_MIN) {          // longer tails: kzg_bulk_kernel
             if (lfill) warp_set_global(out + cur, rle, lit_regen - used, lane);
             else warp_copy_global<false>(out + cur, lit + used, lit_regen - used, lane);
         }
     }
     __threadfence_block();
     __syncwarp();
-    return false;
+    return 0u;
 }
 
+// FULL = false: the hot variant.  It has no code for long overlapping matches (runs); a frame that contains one is
+// put on the deferred list and executed again, from its first block, by the FULL = true variant, which is launched
+// right after over that list only.  Keeping the rare path out of the hot kernel is worth ~5 % of its speed.
+template <bool FULL>
 __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch B) {
     using namespace kzg_ex;
     extern __shared__ uint4 smem4[];
@@ -444,30 +488,32 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch
     if (B.ctr->overflow & 3u) return;
     for (;;) {
         u32 f = 0;
-        if (lane == 0) f = atomicAdd(&B.ctr->ticket_exec, 1u);
+        if (lane == 0) f = atomicAdd(FULL ? &B.ctr->ticket_exec2 : &B.ctr->ticket_exec, 1u);
         f = __shfl_sync(0xFFFFFFFFu, f, 0);
-        if (f >= B.n_frames) break;
+        if (f >= (FULL ? B.ctr->n_defer : B.n_frames)) break;
+        if (FULL) f = B.dlist[f];
         const KzgFrame* fr = &B.frames[f];
         if (fr->status != KZG_OK) continue;
         u8* const fdst = B.dst + B.dst_off[f];
         const u32 nblk = fr->n_blocks, first = fr->first_block;
         bool failed = false;
-        for (u32 k = 0; k < nblk && !failed; k++) {
+        bool deferred = false;
+        for (u32 k = 0; k < nblk && !failed && !deferred; k++) {
             const KzgBlock blk = B.blocks[first + k];
             u8* out = fdst + blk.out_off;
-            if (blk.type == 0) warp_copy_global<false>(out, B.src + blk.src, blk.regen, lane);
-            else if (blk.type == 1) warp_set_global(out, B.src[blk.src], blk.regen, lane);
-            else {
+            // raw / RLE blocks and literal-only blocks were written by kzg_bulk_kernel
+            if (blk.type == 2) {
                 const KzgCBlock* cb = &B.cblocks[blk.cidx];
-                if (cb->n_seq == 0) {
-                    const u8* lit = cb->lit_type >= 2 ? B.lit_pool + cb->lit_out : B.src + cb->src + cb->lit_src;
-                    if (cb->lit_type == 1) warp_set_global(out, lit[0], blk.regen, lane);
-                    else warp_copy_global<false>(out, lit, blk.regen, lane);
-                } else failed = kzg_exec_sequences(B, blk, cb, out, smem, lane);
+                if (cb->n_seq) {
+                    const u32 r = kzg_exec_sequences<FULL>(B, blk, cb, out, smem, lane);
+                    failed = r == 1;
+                    deferred = r == 2;
+                }
             }
             __threadfence_block();
             __syncwarp();
         }
         if (failed && lane == 0) B.frames[f].status = KZG_E_CORRUPTION;
+        if (deferred && lane == 0) B.dlist[atomicAdd(&B.ctr->n_defer, 1u)] = f;      // the full kernel redoes this frame
     }
 }

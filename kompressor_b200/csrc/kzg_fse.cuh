@@ -95,7 +95,7 @@ __device__ __forceinline__ u32 slow_bits(const u32* base32, i32 P, u32 n) {
     return __funnelshift_r(w0, w1, q) >> (32 - n);
 }
 
-struct Result { u32 status, regen, lit_used, rep0, rep1, rep2; };
+struct Result { u32 status, regen, lit_used, rep0, rep1, rep2, bulk_lits; };
 
 // Per-block decode parameters shared by the fast loop and the general fallback.
 struct Job {
@@ -129,6 +129,7 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
     u32 sML = slow_bits(j.base32, P, j.logML); P -= (i32)j.logML;
     if (P < j.lowbits) return;
     u32 rep0 = j.rep0, rep1 = j.rep1, rep2 = j.rep2, lit_end = 0, out_end = 0, ovf = 0;
+    res.bulk_lits = 0;
     for (u32 i = 0; i < j.nseq; i++) {
         const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
         const u32 ofc = eOF & 63u;
@@ -152,6 +153,7 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
         lit_end += ll;
         out_end += ll + ml;
         ovf |= out_end;
+        if (ll >= KZG_BULK_MIN) res.bulk_lits += ll;
         j.out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
         if (i + 1 < j.nseq) {
             const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
             else if (B.dict_entropy) { j.rep0 = B.dict_rep[0]; j.rep1 = B.dict_rep[1]; j.rep2 = B.dict_rep[2]; }
         } else if (chain) { sts16(tLL, 1u << 6); sts16(tOF, 1u << 6); sts16(tML, 1u << 6); }
         Result res;
-        res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0;
+        res.status = KZG_E_CORRUPTION; res.regen = 0; res.lit_used = 0; res.bulk_lits = 0;
         res.rep0 = j.rep0; res.rep1 = j.rep1; res.rep2 = j.rep2;
 
         // ---- bitstream set-up (chain warp); the effective sequence count goes to the post warp
@@ -362,11 +364,12 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
                 cb->regen = res.regen;
                 cb->lit_used = res.lit_used;
                 cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
+                cb->bulk_lits = res.bulk_lits >= KZG_BULK_SUM ? 1u : 0u;
             }
         } else {
             // =================================================================== post warp
             u32 rep0 = j.rep0, rep1 = j.rep1, rep2 = j.rep2;
-            u32 lit_end = 0, out_end = 0, ovf = 0;
+            u32 lit_end = 0, out_end = 0, ovf = 0, longsum = 0;
             u64* out = j.out;
             for (u32 t = 0; t < nint; t++) {
                 const u32 buf = t & 1u;
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
                     rep0 = act ? off : rep0;
                     lit_end += ll;
                     out_end += ll + ml;
+                    longsum += ll >= KZG_BULK_MIN ? ll : 0u;
                     ovf |= out_end;           // one sequence adds < 2^18, so any overflow past 2^18 leaves a high bit here
                     if (act) out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
                 }
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
                 cb->regen = res.regen;
                 cb->lit_used = res.lit_used;
                 cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
+                cb->bulk_lits = longsum >= KZG_BULK_SUM ? 1u : 0u;
             }
         }
 #undef KZG_FSE_WINDOW

@@ -9,8 +9,9 @@
 //   huffman   thread / stream       table build (4 lanes per table) + 4-stream literal decode (s3)
 //   fse       thread / block        table build + sequential ZSTD_decodeSequence state machine (s4)
 //   offsets   thread / frame        per-block output offsets, repeat-offset hand-over, size checks
-//   execute   CTA / frame           raw + RLE blocks, literal + match copy through a shared-memory
-//                                   output tile, 16-byte vectorised flush                    (s2, s5)
+//   bulk      CTA / block           raw + RLE blocks, literal-only blocks, long literal runs            (s2, s5)
+//   execute   warp / frame          literal + match copy through a shared-memory output window,
+//                                   16-byte vectorised flush                                       (s5)
 //   finish    4 lanes / frame       XXH64 of the output, checksum compare, status + size      (s6)
 //
 // The format logic follows RFC 8878 / SURVEY.md Appendix A; it replaces what libzstd does underneath
@@ -20,6 +21,7 @@
 #include "kzg_huf.cuh"
 #include "kzg_fsetab.cuh"
 #include "kzg_fse.cuh"
+#include "kzg_bulk.cuh"
 #include "kzg_exec.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
 // ------------------------------------------------------------------------------------------------
 static bool g_attr_done = false;
 
-const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fsetab", "huffman", "fse", "offsets", "execute", "finish" };
+const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fsetab", "huffman", "fse", "offsets", "bulk", "execute", "execute_runs", "finish" };
 
 int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
     const size_t huf_smem = KZG_HUF_SMEM;
@@ -154,7 +156,8 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
     if (!g_attr_done) {
         cudaFuncSetAttribute(kzg_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem);
         cudaFuncSetAttribute(kzg_fse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fse_smem);
-        cudaFuncSetAttribute(kzg_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exec_smem);
+        cudaFuncSetAttribute(kzg_exec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exec_smem);
+        cudaFuncSetAttribute(kzg_exec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exec_smem);
         g_attr_done = true;
     }
     const u32 n = b.n_frames;
@@ -178,8 +181,12 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
     KZG_MARK();
     kzg_offsets_kernel<<<fgrid, 128, 0, stream>>>(b);
     KZG_MARK();
+    kzg_bulk_kernel<<<sm_count * 4, KZG_BULK_THREADS, 0, stream>>>(b);
+    KZG_MARK();
     const int exec_per_sm = (int)((227 * 1024) / (exec_smem + 1024));
-    kzg_exec_kernel<<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
+    kzg_exec_kernel<false><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
+    KZG_MARK();
+    kzg_exec_kernel<true><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);     // deferred frames only
     KZG_MARK();
     kzg_finish_kernel<<<(n * 4 + 127) / 128, 128, 0, stream>>>(b);
     KZG_MARK();

@@ -6,7 +6,7 @@
 struct KzgLaunchInfo { int sm_count; int launches; };
 
 // Enqueues the whole decode pipeline for one batch on `stream`. Returns number of kernel launches.
-#define KZG_N_STAGES 9
+#define KZG_N_STAGES 11
 // If ev != nullptr it must hold KZG_N_STAGES + 1 events; event k is recorded before stage k.
 int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev);
 extern const char* const kzg_stage_names[KZG_N_STAGES];

@@ -108,6 +108,7 @@ KZG_HD void kzg_stage_parse(const KzgBatch& B, u32 c) {
     cb.rep_init[0] = 1; cb.rep_init[1] = 4; cb.rep_init[2] = 8;
     cb.rep_final[0] = 1; cb.rep_final[1] = 4; cb.rep_final[2] = 8;
     cb.first_in_frame = 0;
+    cb.bulk_lits = 0;
     if (cb.status_lit == KZG_OK && cb.lit_type >= 2) {
         const u64 sz = ((u64)cb.lit_regen + 31) & ~15ull;
         const u64 off = KZG_ATOMIC_ADD64(&B.ctr->lit_used, sz);
@@ -195,6 +196,7 @@ KZG_HD void kzg_stage_fse_block(const KzgBatch& B, KzgCBlock* cb, u16* tLL, u16*
     cb->regen = res.regen;
     cb->lit_used = res.lit_used;
     cb->rep_final[0] = res.rep0; cb->rep_final[1] = res.rep1; cb->rep_final[2] = res.rep2;
+    cb->bulk_lits = res.bulk_lits >= KZG_BULK_SUM ? 1u : 0u;
 }
 
 KZG_HD u32 kzg_rep_subst(u32 enc, const u32* rep) {
@@ -237,4 +239,15 @@ KZG_HD void kzg_stage_offsets(const KzgBatch& B, u32 i) {
     if (!err && fr->fcs != ~0ull && pos != fr->fcs) err = KZG_E_CORRUPTION;
     fr->status = err;
     fr->out_size = err ? 0 : pos;
+    if (err) return;
+    // work list of the bulk kernel: raw / RLE blocks, literal-only blocks, long literal tails and runs
+    for (u32 k = 0; k < fr->n_blocks; k++) {
+        const KzgBlock* blk = &B.blocks[fr->first_block + k];
+        bool bulk = blk->type != 2;
+        if (!bulk) {
+            const KzgCBlock* cb = &B.cblocks[blk->cidx];
+            bulk = cb->n_seq == 0 || cb->lit_regen - cb->lit_used >= KZG_BULK_MIN || cb->bulk_lits;
+        }
+        if (bulk && blk->regen) B.blist[KZG_ATOMIC_ADD32(&B.ctr->n_bulk, 1u)] = fr->first_block + k;
+    }
 }

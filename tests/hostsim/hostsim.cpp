@@ -47,7 +47,7 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     std::vector<KzgCBlock> cblocks(block_cap);
     std::vector<KzgFseDesc> fse(block_cap);
     std::vector<KzgHufDesc> huf(block_cap);
-    std::vector<u32> hlist(block_cap), slist(block_cap);
+    std::vector<u32> hlist(block_cap), slist(block_cap), blist(block_cap);
     std::vector<u8> lit(total_dst + 64 * block_cap + 4096 + 16);
     std::vector<u64> seq(total_dst / 3 + 4096);
     KzgCounters ctr;
@@ -61,7 +61,7 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     B.src = src; B.src_off = src_off; B.src_size = src_size; B.dst = dst; B.dst_off = dst_off; B.dst_cap = dst_cap;
     B.status = status; B.out_size = out_size; B.n_frames = (u32)n; B.tile_bytes = KZG_BLOCK_MAX + 64;
     B.frames = frames.data(); B.blocks = blocks.data(); B.cblocks = cblocks.data(); B.fse = fse.data(); B.huf = huf.data();
-    B.hlist = hlist.data(); B.slist = slist.data();
+    B.hlist = hlist.data(); B.slist = slist.data(); B.blist = blist.data();
     B.lit_pool = (u8*)(((uintptr_t)lit.data() + 15) & ~(uintptr_t)15); B.seq_pool = seq.data(); B.ctr = &ctr;
     B.fse_default = &def; B.code_tables = codes; B.lit_cap = lit.size() - 32; B.seq_cap = seq.size();
     B.block_cap = (u32)block_cap; B.cblock_cap = (u32)block_cap;

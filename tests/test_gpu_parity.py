@@ -204,4 +204,4 @@ def test_device_resident_batch_and_size_independent_properties(dec):
     h_exp = hashlib.sha256(b"".join(hashlib.sha256(r.tobytes()).digest() for r in exp)).hexdigest()
     assert h_got == h_exp
     st = dec.stats()
-    assert st.n_cblocks == n and st.launches == 9
+    assert st.n_cblocks == n and st.launches == 11
