@@ -27,7 +27,8 @@ for ln in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
     if m:
         line_of[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", re.sub(r"^_Z\d+", "", kern).split("8KzgBatch")[0]],
+base_name = re.split(r"IL|Ev8KzgBatch|8KzgBatch", re.sub(r"^_Z\d+", "", kern))[0]      # ncu matches the un-templated name
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", base_name, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
