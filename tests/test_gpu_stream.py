@@ -126,3 +126,53 @@ def test_tiny_output_slices_and_byte_at_a_time_input(api, libzstd):
         if pos >= len(compressed):
             break
     assert bytes(out) == data
+
+
+def test_many_handles_in_parallel(api, libzstd):
+    """One handle per thread, as one per HTTP body (SURVEY.md section 8(b) 'Threading'): the shim merges the
+    frames of concurrent calls into shared GPU batches; every stream must still see exactly its own bytes,
+    its own dictionary and its own errors."""
+    import threading
+    import corpus
+    core, io, zstd = api
+    dictionary = libzstd.train_dictionary([bytes(corpus.generate("logs", 300 + i, 1500)) for i in range(200)], 8192)
+    raw_dict = b"level=INFO component=scheduler thread=worker-"
+    jobs = []
+    for t in range(24):
+        kind = ("logs", "json", "literal")[t % 3]
+        frames = [bytes(corpus.generate(kind, 1000 + 17 * t + i, 20000 + 3001 * ((t + i) % 5))) for i in range(6)]
+        d = (None, dictionary, raw_dict)[t % 4] if t % 4 < 3 else None
+        comp = b"".join(libzstd.compress(f, 3, checksum=bool(t & 1), dictionary=d) for f in frames)
+        jobs.append(dict(data=b"".join(frames), comp=comp, dict=d, mode="pipe" if t % 2 else "transform", bad=False))
+    big = bytes(corpus.generate("logs", 4242, 24 << 20))          # a large request that runs alone between the merged ones
+    jobs.append(dict(data=big, comp=b"".join(libzstd.compress(big[i:i + (1 << 20)], 3) for i in range(0, len(big), 1 << 20)),
+                     dict=None, mode="transform", bad=False))
+    broken = bytearray(b"".join(libzstd.compress(bytes(corpus.generate("logs", 9000 + i, 30000)), 3, checksum=True) for i in range(4)))
+    broken[200] ^= 0x55                                          # inside the first frame's literals: corruption or checksum error
+    jobs.append(dict(data=None, comp=bytes(broken), dict=None, mode="pipe", bad=True))
+    results = [None] * len(jobs)
+
+    def work(i):
+        j = jobs[i]
+        try:
+            for _ in range(3):
+                dec = zstd.ZstdDecompressor(dictionary=j["dict"])
+                out = core.transform(dec, j["comp"]) if j["mode"] == "transform" else io.pipe(j["comp"], dec).readByteArray()
+                dec.close()
+                if out != j["data"]:
+                    results[i] = "mismatch"
+                    return
+            results[i] = "ok"
+        except zstd.IllegalStateException as e:
+            results[i] = f"error {e.code}"
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i, j in enumerate(jobs):
+        if j["bad"]:
+            assert results[i] is not None and results[i].startswith("error"), (i, results[i])
+        else:
+            assert results[i] == "ok", (i, results[i])
