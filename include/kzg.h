@@ -109,6 +109,35 @@ int kzg_ctx_set_dictionary(kzg_ctx* ctx, const void* dict, size_t size);
 int kzg_ctx_set_profiling(kzg_ctx* ctx, int enable);
 int kzg_last_stage_ms(kzg_ctx* ctx, float* ms, const char** names, int max_stages);
 
+/* ------------------------------------------------------------------ Layer A, compress side: batch frame writer
+ * SURVEY.md section 8(f) rank 4, the step before the path.  Replaces, for producers that hold many chunks,
+ * ZSTD_compressStream2 behind Java_..._ZstdWrapper_compressStream (Wrapper.cpp:75-121, ZstdWrapper.kt:26-46):
+ * every chunk (at most 128 KiB; 64 KiB is the shape the decoder is measured on) becomes one independent
+ * single-block zstd frame with its content size in the header, i.e. exactly what layer A decodes in bulk.
+ * Any conforming decoder (libzstd included) reads the output. */
+typedef struct kzg_enc kzg_enc;
+int kzg_enc_create(kzg_enc** out, int device);                 /* device < 0: current device */
+void kzg_enc_destroy(kzg_enc* enc);
+size_t kzg_compress_bound(size_t src_size);                    /* capacity every chunk's frame needs (ZSTD_compressBound's role) */
+#define KZG_COMPRESS_CHECKSUM 1                                /* flags: append the XXH64 content checksum (ZSTD_c_checksumFlag) */
+
+/* Compresses n chunks resident in device memory: chunk i is d_src + d_src_off[i], d_src_size[i] bytes; its frame
+ * goes to d_dst + d_dst_off[i] (capacity d_dst_cap[i] >= kzg_compress_bound(size), else status 70).
+ * d_status[i]: 0 or ZSTD_ErrorCode (72 = chunk larger than 128 KiB); d_out_size[i]: frame bytes.
+ * max_chunk = largest d_src_size (host-side, sizes the workspace).  The 16-byte aligned chunks around every byte
+ * of d_src must be readable.  Enqueued on `cuda_stream` (NULL: the encoder's own), not synchronised: call
+ * kzg_enc_finish.  Returns the number of kernels launched or a negative code. */
+int kzg_compress_batch_device(kzg_enc* enc, const void* d_src, const uint64_t* d_src_off, const uint64_t* d_src_size,
+                              void* d_dst, const uint64_t* d_dst_off, const uint64_t* d_dst_cap, uint64_t n,
+                              uint64_t max_chunk, int flags, uint32_t* d_status, uint64_t* d_out_size, void* cuda_stream);
+int kzg_enc_finish(kzg_enc* enc, void* cuda_stream);
+/* Same with host memory (synchronous). */
+int kzg_compress_batch_host(kzg_enc* enc, const void* src, const uint64_t* src_off, const uint64_t* src_size,
+                            void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n, int flags,
+                            uint32_t* status, uint64_t* out_size);
+int kzg_enc_set_profiling(kzg_enc* enc, int enable);
+int kzg_enc_last_stage_ms(kzg_enc* enc, float* ms, const char** names, int max_stages);
+
 /* ------------------------------------------------------------------ Layer B: streaming shim */
 typedef struct kzg_DCtx kzg_DCtx;
 typedef struct { const void* src; size_t size; size_t pos; } kzg_inBuffer;   /* == ZSTD_inBuffer */

@@ -36,6 +36,8 @@ EXPORTS = [
     "kzg_isError", "kzg_getErrorName", "kzg_versionString", "kzg_ctx_create", "kzg_ctx_destroy", "kzg_scan_frames",
     "kzg_decompress_batch_device", "kzg_batch_finish", "kzg_decompress_batch_host", "kzg_host_alloc", "kzg_host_free",
     "kzg_last_batch_stats", "kzg_ctx_set_dictionary", "kzg_ctx_set_profiling", "kzg_last_stage_ms", "kzg_createDCtx", "kzg_freeDCtx", "kzg_DCtx_loadDictionary", "kzg_decompressStream",
+    "kzg_enc_create", "kzg_enc_destroy", "kzg_compress_bound", "kzg_compress_batch_device", "kzg_enc_finish",
+    "kzg_compress_batch_host", "kzg_enc_set_profiling", "kzg_enc_last_stage_ms",
 ]
 
 _lib = None
@@ -80,6 +82,24 @@ def lib() -> ctypes.CDLL:
     L.kzg_ctx_set_profiling.restype = c_int
     L.kzg_last_stage_ms.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
     L.kzg_last_stage_ms.restype = c_int
+    L.kzg_enc_create.argtypes = [POINTER(c_void_p), c_int]
+    L.kzg_enc_create.restype = c_int
+    L.kzg_enc_destroy.argtypes = [c_void_p]
+    L.kzg_enc_destroy.restype = None
+    L.kzg_compress_bound.argtypes = [c_size_t]
+    L.kzg_compress_bound.restype = c_size_t
+    L.kzg_compress_batch_device.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64,
+                                            c_uint64, c_int, c_void_p, c_void_p, c_void_p]
+    L.kzg_compress_batch_device.restype = c_int
+    L.kzg_enc_finish.argtypes = [c_void_p, c_void_p]
+    L.kzg_enc_finish.restype = c_int
+    L.kzg_compress_batch_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64,
+                                          c_int, c_void_p, c_void_p]
+    L.kzg_compress_batch_host.restype = c_int
+    L.kzg_enc_set_profiling.argtypes = [c_void_p, c_int]
+    L.kzg_enc_set_profiling.restype = c_int
+    L.kzg_enc_last_stage_ms.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
+    L.kzg_enc_last_stage_ms.restype = c_int
     if hasattr(L, "kzg_createDCtx"):
         L.kzg_createDCtx.restype = c_void_p
         L.kzg_freeDCtx.argtypes = [c_void_p]

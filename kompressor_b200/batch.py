@@ -161,3 +161,74 @@ class BatchDecoder:
         st = BatchStats()
         self._L.kzg_last_batch_stats(self._h, ctypes.byref(st))
         return st
+
+
+class BatchEncoder:
+    """Batch frame writer on one GPU (include/kzg.h, kzg_compress_batch_*): every chunk of at most 128 KiB becomes
+    one independent single-block zstd frame, the shape BatchDecoder decodes in bulk.  The step before the path
+    (reference: ZstdWrapper.compressStream, ZstdWrapper.kt:26-46 -> Wrapper.cpp:75-121)."""
+
+    def __init__(self, device: int = -1):
+        self._L = lib()
+        h = ctypes.c_void_p()
+        rc = self._L.kzg_enc_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise KzgError(f"kzg_enc_create failed with code {rc} (a CUDA device is required; there is no CPU fallback)")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kzg_enc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bound(self, n: int) -> int:
+        return int(self._L.kzg_compress_bound(n))
+
+    def compress_chunks(self, data: np.ndarray, offsets: np.ndarray, sizes: np.ndarray, checksum: bool = False):
+        """Host memory in, host memory out -> (buffer, frame offsets, frame sizes, status)."""
+        n = int(len(offsets))
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        caps = np.array([self.bound(int(s)) for s in sizes], dtype=np.uint64) if n else np.zeros(0, np.uint64)
+        caps = (caps + 15) & ~np.uint64(15)
+        doff = np.zeros(n, np.uint64)
+        if n:
+            doff[1:] = np.cumsum(caps)[:-1]
+        out = np.zeros(int(caps.sum()) + 64, np.uint8)
+        status = np.zeros(n, np.uint32)
+        out_size = np.zeros(n, np.uint64)
+        rc = self._L.kzg_compress_batch_host(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data,
+                                             sizes.ctypes.data, out.ctypes.data, doff.ctypes.data, caps.ctypes.data, n,
+                                             1 if checksum else 0, status.ctypes.data, out_size.ctypes.data)
+        if rc < 0:
+            raise KzgError(f"kzg_compress_batch_host failed: {rc}")
+        return out, doff, out_size, status
+
+    def compress(self, data, chunk_size: int = 65536, checksum: bool = False) -> bytes:
+        """Cuts `data` into chunks of chunk_size and returns the concatenated frames (a valid zstd stream: any
+        decoder yields `data` again)."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        if not 0 < chunk_size <= 131072:
+            raise ValueError("chunk_size must be in (0, 131072]")
+        n = max(1, (a.size + chunk_size - 1) // chunk_size)
+        offsets = np.arange(n, dtype=np.uint64) * np.uint64(chunk_size)
+        sizes = np.minimum(np.uint64(chunk_size), np.uint64(a.size) - offsets).astype(np.uint64) if a.size else np.zeros(1, np.uint64)
+        out, doff, osz, status = self.compress_chunks(a, offsets, sizes, checksum)
+        if status.any():
+            raise KzgError(f"compress failed: status {status[status != 0][0]}")
+        return b"".join(out[int(o):int(o) + int(s)].tobytes() for o, s in zip(doff, osz))
+
+    def set_profiling(self, enable: bool = True) -> None:
+        self._L.kzg_enc_set_profiling(self._h, int(enable))
+
+    def stage_ms(self) -> dict:
+        ms = (ctypes.c_float * 4)()
+        names = (ctypes.c_char_p * 4)()
+        n = self._L.kzg_enc_last_stage_ms(self._h, ms, names, 4)
+        return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkzg.so")
-SOURCES = ["kzg_kernels.cu", "kzg_api.cu", "kzg_stream.cu"]
+SOURCES = ["kzg_kernels.cu", "kzg_api.cu", "kzg_stream.cu", "kzg_enc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr"]
 

@@ -1,0 +1,209 @@
+// C ABI of the batch frame writer (include/kzg.h, "Layer A, compress side"): kzg_enc_* and kzg_compress_batch_*.
+// Kernels and format notes: kzg_enc.cuh.
+#include "../../include/kzg.h"
+#include "kzg_enc.cuh"
+
+#include <cuda_runtime.h>
+#include <mutex>
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct kzg_enc {
+    int device = 0;
+    int sm_count = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    Buf tables, seq, chunks, tickets;            // workspace
+    Buf st_src, st_dst, st_tab;                  // staging of the host-pointer API
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    float stage_ms[3] = { 0, 0, 0 };
+    bool profiling = false;
+};
+
+#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "kzg: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -(int)KZG_E_MEMORY; } } while (0)
+
+extern "C" size_t kzg_compress_bound(size_t src_size) { return (size_t)kzg_enc_bound(src_size); }
+
+extern "C" int kzg_enc_create(kzg_enc** out, int device) {
+    if (!out) return -(int)KZG_E_GENERIC;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return -(int)KZG_E_MEMORY; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= count) return -(int)KZG_E_GENERIC;
+    CKE(cudaSetDevice(device));
+    kzg_enc* e = new (std::nothrow) kzg_enc();
+    if (!e) return -(int)KZG_E_MEMORY;
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
+    for (int k = 0; k < 4; k++) cudaEventCreate(&e->ev[k]);
+    static KzgEncTables host_tables;
+    kzg_enc_build_tables(host_tables);
+    if (e->tables.ensure(sizeof(KzgEncTables)) || e->tickets.ensure(64) ||
+        cudaMemcpy(e->tables.p, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice) != cudaSuccess) {
+        kzg_enc_destroy(e);
+        return -(int)KZG_E_MEMORY;
+    }
+    cudaFuncSetAttribute(kzg_enc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KZG_ENC_WARPS * (4 << KZG_ENC_HASH_LOG));
+    *out = e;
+    return 0;
+}
+
+extern "C" void kzg_enc_destroy(kzg_enc* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    for (int k = 0; k < 4; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    e->tables.release(); e->seq.release(); e->chunks.release(); e->tickets.release();
+    e->st_src.release(); e->st_dst.release(); e->st_tab.release();
+    delete e;
+}
+
+extern "C" int kzg_enc_set_profiling(kzg_enc* e, int enable) { if (!e) return -(int)KZG_E_GENERIC; e->profiling = enable != 0; return 0; }
+
+extern "C" int kzg_enc_last_stage_ms(kzg_enc* e, float* ms, const char** names, int max_stages) {
+    static const char* const kNames[3] = { "match", "encode", "finish" };
+    if (!e) return -(int)KZG_E_GENERIC;
+    int n = max_stages < 3 ? max_stages : 3;
+    for (int k = 0; k < n; k++) { if (ms) ms[k] = e->stage_ms[k]; if (names) names[k] = kNames[k]; }
+    return n;
+}
+
+// Enqueues the three kernels on `s`. All pointers are device pointers.
+static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, const uint64_t* d_src_size, void* d_dst,
+                   const uint64_t* d_dst_off, const uint64_t* d_dst_cap, uint64_t n, uint64_t max_chunk, int flags,
+                   uint32_t* d_status, uint64_t* d_out_size, cudaStream_t s) {
+    if (n == 0) return 0;
+    if (n > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
+    if (max_chunk > KZG_BLOCK_MAX) max_chunk = KZG_BLOCK_MAX;       // larger chunks are reported per chunk (srcSize_wrong)
+    const u32 seq_cap = (u32)(max_chunk / 8 + 64);
+    if (e->seq.ensure((size_t)n * seq_cap * 8) || e->chunks.ensure((size_t)n * sizeof(KzgEncChunk))) return -(int)KZG_E_MEMORY;
+    KzgEncBatch B;
+    memset(&B, 0, sizeof B);
+    B.src = (const u8*)d_src; B.src_off = d_src_off; B.src_size = d_src_size;
+    B.dst = (u8*)d_dst; B.dst_off = d_dst_off; B.dst_cap = d_dst_cap;
+    B.status = d_status; B.out_size = d_out_size; B.n = (u32)n; B.flags = (u32)flags;
+    B.seq = (u64*)e->seq.p; B.seq_cap = seq_cap; B.chunks = (KzgEncChunk*)e->chunks.p;
+    B.tab = (const KzgEncTables*)e->tables.p; B.tickets = (u32*)e->tickets.p;
+    CKE(cudaMemsetAsync(e->tickets.p, 0, 64, s));
+    const int smem = KZG_ENC_WARPS * (4 << KZG_ENC_HASH_LOG);
+    const int per_sm = (227 * 1024) / (smem + 1024);
+    const bool prof = e->profiling;
+    if (prof) cudaEventRecord(e->ev[0], s);
+    kzg_enc_match_kernel<<<e->sm_count * per_sm, KZG_ENC_WARPS * 32, smem, s>>>(B);
+    if (prof) cudaEventRecord(e->ev[1], s);
+    kzg_enc_encode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(B);
+    if (prof) cudaEventRecord(e->ev[2], s);
+    kzg_enc_finish_kernel<<<e->sm_count * 8, 128, 0, s>>>(B);
+    if (prof) cudaEventRecord(e->ev[3], s);
+    CKE(cudaGetLastError());
+    return 3;
+}
+
+extern "C" int kzg_compress_batch_device(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, const uint64_t* d_src_size,
+                                         void* d_dst, const uint64_t* d_dst_off, const uint64_t* d_dst_cap, uint64_t n,
+                                         uint64_t max_chunk, int flags, uint32_t* d_status, uint64_t* d_out_size, void* stream) {
+    if (!e) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(e->mu);
+    CKE(cudaSetDevice(e->device));
+    return enqueue(e, d_src, d_src_off, d_src_size, d_dst, d_dst_off, d_dst_cap, n, max_chunk, flags, d_status, d_out_size,
+                   stream ? (cudaStream_t)stream : e->stream);
+}
+
+extern "C" int kzg_enc_finish(kzg_enc* e, void* stream) {
+    if (!e) return -(int)KZG_E_GENERIC;
+    std::lock_guard<std::mutex> lock(e->mu);
+    CKE(cudaSetDevice(e->device));
+    CKE(cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
+    if (e->profiling)
+        for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&e->stage_ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) { cudaGetLastError(); e->stage_ms[k] = 0; }
+    return 0;
+}
+
+extern "C" int kzg_compress_batch_host(kzg_enc* e, const void* src, const uint64_t* src_off, const uint64_t* src_size,
+                                       void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n, int flags,
+                                       uint32_t* status, uint64_t* out_size) {
+    if (!e) return -(int)KZG_E_GENERIC;
+    if (n == 0) return 0;
+    std::unique_lock<std::mutex> lock(e->mu);
+    CKE(cudaSetDevice(e->device));
+    u64 src_lo = ~0ull, src_hi = 0, dst_lo = ~0ull, dst_hi = 0, max_chunk = 0;
+    for (u64 i = 0; i < n; i++) {
+        if (src_off[i] < src_lo) src_lo = src_off[i];
+        if (src_off[i] + src_size[i] > src_hi) src_hi = src_off[i] + src_size[i];
+        if (dst_off[i] < dst_lo) dst_lo = dst_off[i];
+        if (dst_off[i] + dst_cap[i] > dst_hi) dst_hi = dst_off[i] + dst_cap[i];
+        if (src_size[i] > max_chunk) max_chunk = src_size[i];
+    }
+    const u64 src_span = src_hi - src_lo, dst_span = dst_hi - dst_lo;
+    const u64 tab_bytes = n * (5 * 8 + 4);
+    if (e->st_src.ensure(src_span + 64) || e->st_dst.ensure(dst_span + 64) || e->st_tab.ensure(tab_bytes + 64)) return -(int)KZG_E_MEMORY;
+    u64* t_off = (u64*)e->st_tab.p;
+    u64* t_size = t_off + n;
+    u64* t_doff = t_size + n;
+    u64* t_dcap = t_doff + n;
+    u64* t_osize = t_dcap + n;
+    u32* t_status = (u32*)(t_osize + n);
+    u64* h_tab = (u64*)malloc(n * 4 * 8);
+    if (!h_tab) return -(int)KZG_E_MEMORY;
+    for (u64 i = 0; i < n; i++) {
+        h_tab[i] = src_off[i] - src_lo; h_tab[n + i] = src_size[i];
+        h_tab[2 * n + i] = dst_off[i] - dst_lo; h_tab[3 * n + i] = dst_cap[i];
+    }
+    cudaStream_t s = e->stream;
+    bool ok = cudaMemcpyAsync(e->st_tab.p, h_tab, n * 4 * 8, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+              cudaMemcpyAsync(e->st_src.p, (const u8*)src + src_lo, src_span, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    int rc = 0;
+    if (ok) {
+        rc = enqueue(e, e->st_src.p, t_off, t_size, e->st_dst.p, t_doff, t_dcap, n, max_chunk, flags, t_status, t_osize, s);
+        ok = rc >= 0 && cudaMemcpyAsync(status, t_status, n * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+             cudaMemcpyAsync(out_size, t_osize, n * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+             cudaStreamSynchronize(s) == cudaSuccess;
+    }
+    if (ok) {
+        // copy back either what each frame occupies (sizes are known now) or, when there are many frames, whole
+        // capacity regions with adjacent ones coalesced (one copy per run instead of one per frame)
+        u64 total_out = 0, total_cap = 0;
+        for (u64 i = 0; i < n; i++) { total_out += status[i] == 0 ? out_size[i] : 0; total_cap += dst_cap[i]; }
+        const bool exact = (double)n * 3e-6 + (double)total_out / 50e9 < (double)total_cap / 50e9;
+        u64 run_lo = 0, run_hi = 0;
+        bool open = false;
+        for (u64 i = 0; ok && i <= n; i++) {
+            const u64 len = i < n ? (exact ? (status[i] == 0 ? out_size[i] : 0) : dst_cap[i]) : 0;
+            const bool have = i < n && len > 0;
+            if (have && open && dst_off[i] == run_hi) { run_hi += len; continue; }
+            if (open) ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)e->st_dst.p + (run_lo - dst_lo), run_hi - run_lo, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            open = have;
+            if (have) { run_lo = dst_off[i]; run_hi = dst_off[i] + len; }
+        }
+        ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    }
+    free(h_tab);
+    if (rc < 0) return rc;
+    if (!ok) { cudaGetLastError(); return -(int)KZG_E_MEMORY; }
+    if (e->profiling)
+        for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&e->stage_ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) { cudaGetLastError(); e->stage_ms[k] = 0; }
+    return 0;
+}

@@ -48,3 +48,29 @@ def run(frames, caps):
                                   osz.ctypes.data, None, 0, None, 0)
     assert r == 0, r
     return [bytes(dst[int(doffs[i]):int(doffs[i] + osz[i])]) for i in range(n)], status, osz
+
+
+def compress(chunks, checksum=False):
+    """Compresses `chunks` (list of bytes, each <= 128 KiB) with the host-compiled encode stage behind a sequential
+    matcher -> (frames, status)."""
+    global _lib
+    if _lib is None:
+        run([], [])
+    _lib.kzs_compress_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    n = len(chunks)
+    blob = b"".join(chunks)
+    src = np.frombuffer(blob + b"\0" * 16, dtype=np.uint8).copy()
+    sizes = np.array([len(c) for c in chunks], dtype=np.uint64)
+    offs = np.zeros(n, np.uint64)
+    offs[1:] = np.cumsum(sizes)[:-1]
+    caps = sizes + np.uint64(32)
+    doffs = np.zeros(n, np.uint64)
+    doffs[1:] = np.cumsum(caps)[:-1]
+    dst = np.zeros(int(caps.sum()) + 64, np.uint8)
+    status = np.zeros(n, np.uint32)
+    osz = np.zeros(n, np.uint64)
+    r = _lib.kzs_compress_batch(src.ctypes.data, offs.ctypes.data, sizes.ctypes.data, n, dst.ctypes.data, doffs.ctypes.data,
+                                caps.ctypes.data, 1 if checksum else 0, status.ctypes.data, osz.ctypes.data)
+    assert r == 0, r
+    return [bytes(dst[int(doffs[i]):int(doffs[i] + osz[i])]) for i in range(n)], status

@@ -128,3 +128,72 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Compress side: a sequential stand-in for the warp-cooperative match kernel (same record format, same literal
+// placement), then the very encode stage the GPU runs (kzg_enc_stage_encode), then the finish step in plain C.
+#include "../../kompressor_b200/csrc/kzg_enc.cuh"
+
+extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* src_size, u64 n, u8* dst, const u64* dst_off,
+                                  const u64* dst_cap, int flags, u32* status, u64* out_size) {
+    static KzgEncTables tables;
+    kzg_enc_build_tables(tables);
+    u64 max_chunk = 0;
+    for (u64 i = 0; i < n; i++) if (src_size[i] > max_chunk) max_chunk = src_size[i];
+    if (max_chunk > KZG_BLOCK_MAX) max_chunk = KZG_BLOCK_MAX;
+    const u32 seq_cap = (u32)(max_chunk / 8 + 64);
+    std::vector<u64> seq((size_t)n * seq_cap);
+    std::vector<KzgEncChunk> chunks(n);
+    KzgEncBatch B;
+    memset(&B, 0, sizeof B);
+    B.src = src; B.src_off = src_off; B.src_size = src_size; B.dst = dst; B.dst_off = dst_off; B.dst_cap = dst_cap;
+    B.status = status; B.out_size = out_size; B.n = (u32)n; B.flags = (u32)flags;
+    B.seq = seq.data(); B.seq_cap = seq_cap; B.chunks = chunks.data(); B.tab = &tables;
+    std::vector<u32> table(1u << KZG_ENC_HASH_LOG);
+    for (u32 i = 0; i < n; i++) {
+        KzgEncChunk& ck = chunks[i];
+        ck.n_seq = 0; ck.lit_size = 0; ck.state = 0; ck.total = 0;
+        const u32 len = (u32)src_size[i];
+        if (src_size[i] > KZG_BLOCK_MAX || dst_cap[i] < kzg_enc_bound(len) || len < 64) continue;
+        const u8* s = src + src_off[i];
+        u8* lit = dst + dst_off[i] + kzg_enc_header_size(len) + 6;
+        u64* rec = seq.data() + (size_t)i * seq_cap;
+        std::fill(table.begin(), table.end(), 0xFFFFFFFFu);
+        const u32 limit = len - 12;
+        u32 pos = 0, anchor = 0;
+        while (pos < limit && ck.n_seq < seq_cap) {
+            const u32 v = kzg_rd32(s + pos), h = (v * 2654435761u) >> (32 - KZG_ENC_HASH_LOG);
+            const u32 cand = table[h];
+            table[h] = pos;
+            if (cand == 0xFFFFFFFFu || kzg_rd32(s + cand) != v) { pos++; continue; }
+            u32 ml = 4;
+            while (pos + ml < len && s[cand + ml] == s[pos + ml]) ml++;
+            const u32 ll = pos - anchor;
+            memcpy(lit + ck.lit_size, s + anchor, ll);
+            rec[ck.n_seq++] = (u64)ll | ((u64)ml << 18) | ((u64)(pos - cand) << 36);
+            ck.lit_size += ll;
+            anchor = pos = pos + ml;
+        }
+        memcpy(lit + ck.lit_size, s + anchor, len - anchor);
+        ck.lit_size += len - anchor;
+    }
+    for (u32 i = 0; i < n; i++) kzg_enc_stage_encode(B, i);
+    for (u32 i = 0; i < n; i++) {
+        const KzgEncChunk& ck = chunks[i];
+        if (ck.state == KZG_ENC_ST_ERROR) continue;
+        const u32 len = (u32)src_size[i];
+        const u8* s = src + src_off[i];
+        u8* d = dst + dst_off[i];
+        u32 total = ck.total;
+        if (ck.state != KZG_ENC_ST_COMPRESSED) {
+            const u32 hdr = kzg_enc_header_size(len);
+            kzg_wr24(d + hdr, 1u | (len << 3));
+            memcpy(d + hdr + 3, s, len);
+            total = hdr + 3 + len;
+        }
+        if (flags & KZG_ENC_FLAG_CHECKSUM) { kzg_wr32(d + total, (u32)xxh64(s, len)); total += 4; }
+        status[i] = KZG_OK;
+        out_size[i] = total;
+    }
+    return 0;
+}

@@ -57,3 +57,21 @@ def test_dst_too_small_and_ragged_sizes(libzstd):
     assert (status == 0).all() and outs == raws
     outs, status, _ = hostsim.run(frames[5:], [len(r) - 1 for r in raws[5:]])
     assert (status == 70).all()
+
+
+def test_encode_stage_roundtrip_through_libzstd(libzstd):
+    """Compress side (kzg_enc_stage_encode, the code the GPU's encode kernel runs): frames written behind a sequential
+    stand-in matcher must decode with libzstd to the original bytes; empty input gives libzstd's own empty frame."""
+    import corpus
+    chunks = [bytes(corpus.generate(k, 100 + i, sz)) for i, (k, sz) in enumerate(
+        [("logs", 65536), ("json", 65536), ("literal", 65536), ("logs", 131072), ("logs", 1000), ("json", 300), ("logs", 64),
+         ("logs", 10), ("logs", 0)])]
+    chunks += [bytes(np.random.default_rng(1).integers(0, 256, 65536, dtype=np.uint8)), b"a" * 70000, b"abcdefgh" * 9000]
+    for checksum in (False, True):
+        frames, status = hostsim.compress(chunks, checksum=checksum)
+        for c, f, st in zip(chunks, frames, status):
+            assert st == 0
+            out, err = libzstd.decompress_oneshot(f, len(c) + 16)
+            assert err == 0 and out == c
+    assert hostsim.compress([b""])[0][0].hex() == "28b52ffd2000010000"
+    assert len(hostsim.compress([chunks[0]])[0][0]) < 0.4 * 65536
