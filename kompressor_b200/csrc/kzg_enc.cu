@@ -66,7 +66,7 @@ extern "C" int kzg_enc_create(kzg_enc** out, int device) {
         kzg_enc_destroy(e);
         return -(int)KZG_E_MEMORY;
     }
-    cudaFuncSetAttribute(kzg_enc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KZG_ENC_WARPS * (4 << KZG_ENC_HASH_LOG));
+    cudaFuncSetAttribute(kzg_enc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kzg_enc_match_smem(KZG_BLOCK_MAX));
     *out = e;
     return 0;
 }
@@ -98,7 +98,7 @@ static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, con
     if (n == 0) return 0;
     if (n > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
     if (max_chunk > KZG_BLOCK_MAX) max_chunk = KZG_BLOCK_MAX;       // larger chunks are reported per chunk (srcSize_wrong)
-    const u32 seq_cap = (u32)(max_chunk / 8 + 64);
+    const u32 seq_cap = KZG_ENC_WARPS * (u32)(max_chunk / (6 * KZG_ENC_WARPS) + 32);     // per part: one sequence per 6 bytes at most
     if (e->seq.ensure((size_t)n * seq_cap * 8) || e->chunks.ensure((size_t)n * sizeof(KzgEncChunk))) return -(int)KZG_E_MEMORY;
     KzgEncBatch B;
     memset(&B, 0, sizeof B);
@@ -108,13 +108,15 @@ static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, con
     B.seq = (u64*)e->seq.p; B.seq_cap = seq_cap; B.chunks = (KzgEncChunk*)e->chunks.p;
     B.tab = (const KzgEncTables*)e->tables.p; B.tickets = (u32*)e->tickets.p;
     CKE(cudaMemsetAsync(e->tickets.p, 0, 64, s));
-    const int smem = KZG_ENC_WARPS * (4 << KZG_ENC_HASH_LOG);
+    // the chunk area of the match kernel's shared memory: 64 KiB (two chunks per SM) unless the batch has larger chunks
+    const u32 chunk_cap = max_chunk <= 65536 ? 65536u : KZG_BLOCK_MAX;
+    const int smem = (int)kzg_enc_match_smem(chunk_cap);
     const int per_sm = (227 * 1024) / (smem + 1024);
     const bool prof = e->profiling;
     if (prof) cudaEventRecord(e->ev[0], s);
-    kzg_enc_match_kernel<<<e->sm_count * per_sm, KZG_ENC_WARPS * 32, smem, s>>>(B);
+    kzg_enc_match_kernel<<<e->sm_count * per_sm, KZG_ENC_WARPS * 32, smem, s>>>(B, chunk_cap);
     if (prof) cudaEventRecord(e->ev[1], s);
-    kzg_enc_encode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(B);
+    kzg_enc_encode_kernel<<<e->sm_count * 4, KZG_ENC_EWARPS * 32, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[2], s);
     kzg_enc_finish_kernel<<<e->sm_count * 8, 128, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[3], s);

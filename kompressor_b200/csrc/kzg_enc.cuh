@@ -7,16 +7,22 @@
 //
 // Format choices of this first version: one compressed block per frame with raw literals and the predefined
 // FSE tables (Appendix A.6), repeat-offset codes, optional XXH64 trailer; a raw block when that is not smaller.
-//   match    warp per chunk: 32 positions per step probe a 4-byte hash table in shared memory, the first hit
-//            is extended by the whole warp (128 bytes per step), literals go straight to their final place
-//   encode   thread per chunk: offsets -> repeat codes (forward), then the backward FSE bitstream and headers
+//   match    CTA per chunk, the chunk staged in shared memory: each of the eight warps parses one eighth greedily with
+//            its own hash table of 4-byte strings (first filled with every earlier position of the chunk, so that
+//            candidates come from anywhere before): 32 positions probed per step, the first hit extended 128 bytes
+//            per step by the whole warp; then the warps gather the literal runs from shared memory to their final
+//            place in the frame
+//   encode   warp per chunk: offsets -> repeat codes (forward, serial on one lane over coalesced loads), then the
+//            backward FSE bitstream 32 sequences at a time: three lanes run the three state chains, every lane
+//            assembles its sequence's bit fields at a prefix-summed bit offset in shared memory
 //   finish   warp per chunk: raw-block fallback copy, XXH64 trailer, sizes
-// kzg_enc_stage_encode is KZG_HD: tests/hostsim runs the very same code on the CPU behind a sequential matcher.
+// kzg_enc_stage_encode (KZG_HD) is the serial statement of the encode stage: tests/hostsim runs it on the CPU behind
+// a sequential matcher, and the GPU kernel must produce the same bytes for the same sequences.
 #pragma once
 #include "kzg_stages.cuh"
 
-#define KZG_ENC_HASH_LOG 12
-#define KZG_ENC_WARPS 4
+#define KZG_ENC_HASH_LOG 11          // per-warp table: 2048 entries of 16 bits
+#define KZG_ENC_WARPS 8              // = parts per chunk (each warp parses one)
 #define KZG_ENC_FLAG_CHECKSUM 1u
 #define KZG_ENC_ST_RAW 1u            // chunk state after encode: emit a raw block
 #define KZG_ENC_ST_COMPRESSED 2u
@@ -30,17 +36,17 @@ struct KzgEncTables {
     u8 ll_code[64], ml_code[128];                     // code of small literal lengths / (match length - 3)
 };
 
-struct KzgEncChunk { u32 n_seq, lit_size, state, total; };
+struct KzgEncChunk { u32 n_seq[KZG_ENC_WARPS]; u32 lit_size, state, total, pad; };   // n_seq: sequences of each part
 
 struct KzgEncBatch {
     const u8* src; const u64* src_off; const u64* src_size;
     u8* dst; const u64* dst_off; const u64* dst_cap;
     u32* status; u64* out_size;
     u32 n, flags;
-    u64* seq; u32 seq_cap;                            // seq_cap records per chunk: ll[0,18) | ml[18,36) | off[36,54)
+    u64* seq; u32 seq_cap;                            // records per chunk, an eighth of them per part: ll[0,18) | ml[18,36) | off[36,54)
     KzgEncChunk* chunks;
     const KzgEncTables* tab;
-    u32* tickets;                                     // [0] match, [1] finish
+    u32* tickets;                                     // [0] match, [1] finish, [2] encode
 };
 
 KZG_HD void kzg_wr16(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
@@ -139,51 +145,81 @@ KZG_HD void kzg_fsec_encode(KzgBitW& w, KzgFseC& s, const u16* st, const u32* dn
 KZG_HD u32 kzg_enc_ll_code(const KzgEncTables* t, u32 ll) { return ll < 64 ? (u32)t->ll_code[ll] : (u32)kzg_highbit(ll) + 19u; }
 KZG_HD u32 kzg_enc_ml_code(const KzgEncTables* t, u32 mlbase) { return mlbase < 128 ? (u32)t->ml_code[mlbase] : (u32)kzg_highbit(mlbase) + 36u; }
 
-// encode stage, one thread per chunk.  The match stage has left: literals at dst + header + 6, records, counts.
-KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
+// Repeat-offset code of a distance (Appendix A.7); updates the history like the decoder will.
+KZG_HD u32 kzg_enc_offset_value(u32 ll, u32 off, u32& r0, u32& r1, u32& r2) {
+    u32 ob;
+    if (ll) {
+        if (off == r0) return 1;
+        if (off == r1) { r1 = r0; r0 = off; return 2; }
+        ob = off == r2 ? 3u : off + 3u;
+    } else {
+        if (off == r1) { r1 = r0; r0 = off; return 1; }
+        ob = off == r2 ? 2u : (off == r0 - 1 ? 3u : off + 3u);
+    }
+    r2 = r1; r1 = r0; r0 = off;
+    return ob;
+}
+
+// Headers in front of the sequence bitstream. Returns where the bitstream starts, or NULL (raw block / error:
+// ck.state says which).
+KZG_HD u8* kzg_enc_block_prologue(const KzgEncBatch& B, u32 i, u32 nseq, u8*& blk, u8*& limit) {
     const u64 n = B.src_size[i];
     u8* const dst = B.dst + B.dst_off[i];
     KzgEncChunk& ck = B.chunks[i];
-    const bool checksum = (B.flags & KZG_ENC_FLAG_CHECKSUM) != 0;
     ck.total = 0;
-    if (n > KZG_BLOCK_MAX) { ck.state = KZG_ENC_ST_ERROR; B.status[i] = KZG_E_SRCSIZE_WRONG; B.out_size[i] = 0; return; }
-    if (B.dst_cap[i] < kzg_enc_bound(n)) { ck.state = KZG_ENC_ST_ERROR; B.status[i] = KZG_E_DSTSIZE_TOO_SMALL; B.out_size[i] = 0; return; }
-    const u32 hdr = kzg_enc_write_header(dst, n, checksum);
-    const u32 nseq = ck.n_seq, lit_size = ck.lit_size;
+    if (n > KZG_BLOCK_MAX) { ck.state = KZG_ENC_ST_ERROR; B.status[i] = KZG_E_SRCSIZE_WRONG; B.out_size[i] = 0; return nullptr; }
+    if (B.dst_cap[i] < kzg_enc_bound(n)) { ck.state = KZG_ENC_ST_ERROR; B.status[i] = KZG_E_DSTSIZE_TOO_SMALL; B.out_size[i] = 0; return nullptr; }
+    const u32 hdr = kzg_enc_write_header(dst, n, (B.flags & KZG_ENC_FLAG_CHECKSUM) != 0);
+    const u32 lit_size = ck.lit_size;
     ck.state = KZG_ENC_ST_RAW;
-    if (nseq == 0) return;
-    const KzgEncTables* T = B.tab;
-    u8* const blk = dst + hdr + 3;
+    if (nseq == 0) return nullptr;
+    blk = dst + hdr + 3;
     blk[0] = (u8)((3u << 2) | ((lit_size & 15u) << 4));          // raw literals, 20-bit size (3-byte header)
     blk[1] = (u8)(lit_size >> 4);
     blk[2] = (u8)(lit_size >> 12);
     u8* p = blk + 3 + lit_size;
-    u8* const limit = blk + n;                                   // a compressed block must be smaller than the raw one
-    if (p + 4 >= limit) return;
+    limit = blk + n;                                             // a compressed block must be smaller than the raw one
+    if (p + 4 >= limit) return nullptr;
     if (nseq < 128) *p++ = (u8)nseq;
     else if (nseq < 0x7F00) { *p++ = (u8)((nseq >> 8) + 0x80); *p++ = (u8)nseq; }
     else { *p++ = 0xFF; kzg_wr16(p, nseq - 0x7F00); p += 2; }
     *p++ = 0;                                                    // predefined LL / OF / ML tables
+    return p;
+}
+KZG_HD void kzg_enc_block_epilogue(const KzgEncBatch& B, u32 i, u8* blk, u8* end) {
+    u8* const dst = B.dst + B.dst_off[i];
+    const u32 hdr = (u32)(blk - dst) - 3, bsize = (u32)(end - blk);
+    kzg_wr24(dst + hdr, 1u | (2u << 1) | (bsize << 3));
+    B.chunks[i].state = KZG_ENC_ST_COMPRESSED;
+    B.chunks[i].total = hdr + 3 + bsize;
+}
+
+// Record s (in order) of a chunk whose sequences sit in KZG_ENC_WARPS regions of seq_cap / KZG_ENC_WARPS records.
+KZG_HD u64* kzg_enc_seq_at(u64* seq, u32 qcap, const u32* nq, u32 s) {
+    u32 q = 0;
+    while (s >= nq[q]) { s -= nq[q]; q++; }
+    return seq + (size_t)q * qcap + s;
+}
+
+// encode stage, serial statement: one thread per chunk.  The match stage has left: literals at dst + header + 6,
+// records, counts.
+KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
+    KzgEncChunk& ck = B.chunks[i];
+    u32 nq[KZG_ENC_WARPS], nseq = 0;
+    for (u32 q = 0; q < KZG_ENC_WARPS; q++) { nq[q] = ck.n_seq[q]; nseq += nq[q]; }
+    const u32 qcap = B.seq_cap / KZG_ENC_WARPS;
+    u8 *blk = nullptr, *limit = nullptr;
+    u8* p = kzg_enc_block_prologue(B, i, nseq, blk, limit);
+    if (!p) return;
+    const KzgEncTables* T = B.tab;
     u64* seq = B.seq + (size_t)i * B.seq_cap;
-    // forward: distances -> offset values with repeat codes (Appendix A.7), in place
-    {
+    {   // forward: distances -> offset values with repeat codes, in place
         u32 r0 = 1, r1 = 4, r2 = 8;
         for (u32 s = 0; s < nseq; s++) {
-            const u64 rec = seq[s];
-            const u32 ll = (u32)rec & 0x3FFFFu, off = (u32)(rec >> 36) & 0x3FFFFu;
-            u32 ob;
-            if (ll) {
-                if (off == r0) ob = 1;
-                else if (off == r1) { ob = 2; r1 = r0; r0 = off; }
-                else if (off == r2) { ob = 3; r2 = r1; r1 = r0; r0 = off; }
-                else { ob = off + 3; r2 = r1; r1 = r0; r0 = off; }
-            } else {
-                if (off == r1) { ob = 1; r1 = r0; r0 = off; }
-                else if (off == r2) { ob = 2; r2 = r1; r1 = r0; r0 = off; }
-                else if (off == r0 - 1 && off) { ob = 3; r2 = r1; r1 = r0; r0 = off; }
-                else { ob = off + 3; r2 = r1; r1 = r0; r0 = off; }
-            }
-            seq[s] = (rec & 0xFFFFFFFFFull) | ((u64)ob << 36);
+            u64* r = kzg_enc_seq_at(seq, qcap, nq, s);
+            const u64 rec = *r;
+            const u32 ob = kzg_enc_offset_value((u32)rec & 0x3FFFFu, (u32)(rec >> 36) & 0x3FFFFu, r0, r1, r2);
+            *r = (rec & 0xFFFFFFFFFull) | ((u64)ob << 36);
         }
     }
     // backward: the last sequence initialises the states, the first is written last
@@ -191,7 +227,7 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
     w.acc = 0; w.nbits = 0; w.p = p; w.end = limit; w.ovf = false;
     KzgFseC sLL, sML, sOF;
     {
-        const u64 rec = seq[nseq - 1];
+        const u64 rec = *kzg_enc_seq_at(seq, qcap, nq, nseq - 1);
         const u32 ll = (u32)rec & 0x3FFFFu, mlb = ((u32)(rec >> 18) & 0x3FFFFu) - 3u, ob = (u32)(rec >> 36) & 0x3FFFFu;
         const u32 cl = kzg_enc_ll_code(T, ll), cm = kzg_enc_ml_code(T, mlb), co = (u32)kzg_highbit(ob);
         kzg_fsec_init(sML, T->st_ml, T->dnb_ml, T->dfs_ml, cm);
@@ -204,7 +240,7 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
         kzg_bw_flush(w);
     }
     for (u32 s = nseq - 1; s-- > 0;) {
-        const u64 rec = seq[s];
+        const u64 rec = *kzg_enc_seq_at(seq, qcap, nq, s);
         const u32 ll = (u32)rec & 0x3FFFFu, mlb = ((u32)(rec >> 18) & 0x3FFFFu) - 3u, ob = (u32)(rec >> 36) & 0x3FFFFu;
         const u32 cl = kzg_enc_ll_code(T, ll), cm = kzg_enc_ml_code(T, mlb), co = (u32)kzg_highbit(ob);
         kzg_fsec_encode(w, sOF, T->st_of, T->dnb_of, T->dfs_of, co);
@@ -224,16 +260,21 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
     kzg_bw_flush(w);
     if (w.nbits) { if (w.p < w.end) *w.p = (u8)w.acc; else w.ovf = true; w.p++; }
     if (w.ovf || w.p >= limit) return;
-    const u32 bsize = (u32)(w.p - blk);
-    kzg_wr24(dst + hdr, 1u | (2u << 1) | (bsize << 3));
-    ck.state = KZG_ENC_ST_COMPRESSED;
-    ck.total = hdr + 3 + bsize;
+    kzg_enc_block_epilogue(B, i, blk, w.p);
 }
 
 #if defined(__CUDACC__)
 namespace kzg_encd {
 
-// unaligned 32-bit read from two aligned words
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// unaligned 32-bit read from shared memory (two aligned words)
+__device__ __forceinline__ u32 lds32u(u32 a) {
+    const u32 b = a & ~3u;
+    return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) << 3);
+}
+// unaligned 32-bit read from global memory (two aligned words; reads up to 7 bytes past p)
 __device__ __forceinline__ u32 rd32u(const u8* p) {
     const u32* q = reinterpret_cast<const u32*>((uintptr_t)p & ~(uintptr_t)3);
     const u32 sh = ((u32)(uintptr_t)p & 3u) << 3;
@@ -241,8 +282,7 @@ __device__ __forceinline__ u32 rd32u(const u8* p) {
     if (sh == 0) return a;
     return __funnelshift_r(a, q[1], sh);
 }
-
-// warp copy of n bytes, any alignment; reads stay inside [src & ~3, src + n + 3]
+// warp copy of n bytes between global buffers, any alignment; reads stay inside [src & ~3, src + n + 3]
 __device__ __forceinline__ void warp_copy(u8* dst, const u8* src, u32 n, u32 lane) {
     if (n < 64) { for (u32 k = lane; k < n; k += 32) dst[k] = src[k]; return; }
     const u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3);
@@ -253,7 +293,6 @@ __device__ __forceinline__ void warp_copy(u8* dst, const u8* src, u32 n, u32 lan
     for (u32 k = lane; k < nw; k += 32) d4[k] = rd32u(s + 4 * k);
     for (u32 k = head + (nw << 2) + lane; k < n; k += 32) dst[k] = src[k];
 }
-
 // the same for a range that ends at the end of a chunk: the last bytes go one at a time, because warp_copy's
 // word reads may touch up to 3 bytes past its range
 __device__ __forceinline__ void warp_copy_to_end(u8* dst, const u8* src, u32 n, u32 lane) {
@@ -261,83 +300,324 @@ __device__ __forceinline__ void warp_copy_to_end(u8* dst, const u8* src, u32 n, 
     warp_copy(dst, src, n - 8, lane);
     if (lane < 8) dst[n - 8 + lane] = src[n - 8 + lane];
 }
+// warp copy of n bytes from shared memory (address sa) to global memory
+__device__ __forceinline__ void warp_copy_from_smem(u8* dst, u32 sa, u32 n, u32 lane) {
+    if (n < 64) { for (u32 k = lane; k < n; k += 32) dst[k] = (u8)lds8(sa + k); return; }
+    const u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (lane < head) dst[lane] = (u8)lds8(sa + lane);
+    const u32 nw = (n - head) >> 2;
+    u32* d4 = reinterpret_cast<u32*>(dst + head);
+    for (u32 k = lane; k < nw; k += 32) d4[k] = lds32u(sa + head + 4 * k);
+    for (u32 k = head + (nw << 2) + lane; k < n; k += 32) dst[k] = (u8)lds8(sa + k);
+}
+__device__ __forceinline__ u32 warp_incl_sum(u32 v, u32 lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= (u32)o) v += t; }
+    return v;
+}
 
 }  // namespace kzg_encd
 
-// match stage: one warp per chunk, greedy parse with a single-probe hash table of 4-byte strings.
-__global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEncBatch B) {
+// Shared memory of the match kernel: [chunk area: chunk_cap + 32 bytes][one hash table per warp][misc: 128 bytes]
+#define KZG_ENC_TABLE_BYTES (2u << KZG_ENC_HASH_LOG)
+KZG_HD u32 kzg_enc_match_smem(u32 chunk_cap) { return chunk_cap + 32u + KZG_ENC_WARPS * KZG_ENC_TABLE_BYTES + 128u; }
+
+// match stage: one CTA per chunk.
+__global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEncBatch B, u32 chunk_cap) {
     using namespace kzg_encd;
-    extern __shared__ u32 enc_smem[];
+    extern __shared__ uint4 enc_smem4[];
+    u8* const sm = reinterpret_cast<u8*>(enc_smem4);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32* table = enc_smem + (warp << KZG_ENC_HASH_LOG);
+    u16* const table = reinterpret_cast<u16*>(sm + chunk_cap + 32) + (warp << KZG_ENC_HASH_LOG);
+    // misc: [0,8) sequences, [8,16) literal bytes, [16,24) tail literals of the parts, [24] ticket
+    u32* const misc = reinterpret_cast<u32*>(sm + chunk_cap + 32 + KZG_ENC_WARPS * KZG_ENC_TABLE_BYTES);
+    const u32 s_chunk = smem_addr(sm);
     for (;;) {
-        u32 i = 0;
-        if (lane == 0) i = atomicAdd(&B.tickets[0], 1u);
-        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) misc[24] = atomicAdd(&B.tickets[0], 1u);
+        __syncthreads();
+        const u32 i = misc[24];
         if (i >= B.n) break;
         const u32 n = (u32)B.src_size[i];
-        KzgEncChunk ck;
-        ck.n_seq = 0; ck.lit_size = 0; ck.state = 0; ck.total = 0;
-        if (B.src_size[i] > KZG_BLOCK_MAX || B.dst_cap[i] < kzg_enc_bound(n) || n < 64) {     // errors / tiny chunks: raw block
-            if (lane == 0) B.chunks[i] = ck;
+        if (B.src_size[i] > chunk_cap || B.src_size[i] > KZG_BLOCK_MAX || B.dst_cap[i] < kzg_enc_bound(n) || n < 64) {   // errors / tiny chunks: raw block
+            if (threadIdx.x == 0) {
+                KzgEncChunk ck;
+                for (u32 q = 0; q < KZG_ENC_WARPS; q++) ck.n_seq[q] = 0;
+                ck.lit_size = 0; ck.state = 0; ck.total = 0; ck.pad = 0;
+                B.chunks[i] = ck;
+            }
             continue;
         }
-        const u8* s = B.src + B.src_off[i];
-        u8* lit = B.dst + B.dst_off[i] + kzg_enc_header_size(n) + 6;
-        u64* seq = B.seq + (size_t)i * B.seq_cap;
-        for (u32 k = lane; k < (1u << KZG_ENC_HASH_LOG); k += 32) table[k] = 0xFFFFFFFFu;
+        // ---- stage the chunk, keeping its 16-byte phase
+        const u8* g = B.src + B.src_off[i];
+        const u32 shift = (u32)((uintptr_t)g & 15);
+        {
+            const uint4* g4 = reinterpret_cast<const uint4*>(g - shift);
+            const u32 nvec = (shift + n + 15) >> 4;
+            for (u32 v = threadIdx.x; v < nvec; v += blockDim.x) enc_smem4[v] = __ldg(g4 + v);
+        }
+        __syncthreads();
+        const u32 base = s_chunk + shift;                       // shared address of chunk byte 0
+        // ---- this warp's part
+        const u32 qlen = (((n + KZG_ENC_WARPS - 1) / KZG_ENC_WARPS) + 31u) & ~31u;
+        const u32 q0 = min(warp * qlen, n), q1 = min(q0 + qlen, n);
+        const u32 qcap = B.seq_cap / KZG_ENC_WARPS;
+        u64* const seqq = B.seq + (size_t)i * B.seq_cap + (size_t)warp * qcap;
+        // its table starts as "every earlier position of the chunk, inserted in order" (positions keep their low 16 bits)
+        for (u32 k = lane; k < (1u << KZG_ENC_HASH_LOG) / 8; k += 32) reinterpret_cast<uint4*>(table)[k] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        const u32 limit = n - 12;                // positions probed: p + 11 < n, so every read stays inside the chunk
-        u32 pos = 0, anchor = 0, nseq = 0, nlit = 0;
+        for (u32 p0 = 0; p0 < q0; p0 += 32) {                   // q0 is a multiple of 32
+            const u32 p = p0 + lane;
+            const u32 v = lds32u(base + p);
+            table[(v * 2654435761u) >> (32 - KZG_ENC_HASH_LOG)] = (u16)p;
+        }
+        __syncwarp();
+        u32 pos = q0, anchor = q0, nseq = 0, nlit = 0;
+        const u32 limit = q1 >= 3 ? q1 - 3 : 0;                  // probed positions have their 4 bytes inside the part
         while (pos < limit) {
             const u32 p = pos + lane;
             const bool ok = p < limit;
-            const u32 v = ok ? rd32u(s + p) : 0u;
+            const u32 v = lds32u(base + p);
             const u32 h = (v * 2654435761u) >> (32 - KZG_ENC_HASH_LOG);
-            const u32 cand = ok ? table[h] : 0xFFFFFFFFu;
-            const bool hit = cand < p && rd32u(s + cand) == v;
+            // the table keeps the low 16 bits of positions: the candidate is the nearest earlier position with them
+            i32 cand = (i32)((p & ~0xFFFFu) | (u32)table[h]);
+            if (cand >= (i32)p) cand -= 65536;
+            const bool hit = ok && cand >= 0 && lds32u(base + (u32)cand) == v;
             const u32 m = __ballot_sync(0xFFFFFFFFu, hit);
             // positions up to the match start enter the table; the ones behind it are probed again by a later step
             // and must still find their older candidates then
             const u32 l = m ? __ffs(m) - 1 : 31u;
-            if (ok && lane <= l) table[h] = p;
+            if (ok && lane <= l) table[h] = (u16)p;
             __syncwarp();
             if (m == 0) { pos += 32; continue; }
-            const u32 ms = pos + l, mc = __shfl_sync(0xFFFFFFFFu, cand, l);
-            // forward extension, 128 bytes per step
+            const u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
+            // forward extension inside the part, 128 bytes per step
             u32 len = 4;
             for (;;) {
                 const u32 k = len + 4 * lane;
-                const bool in = ms + k + 8 <= n;
-                const u32 diff = in ? (rd32u(s + ms + k) ^ rd32u(s + mc + k)) : 1u;
+                const i32 rem = (i32)q1 - (i32)(ms + k);             // bytes of this lane's word that belong to the part
+                u32 diff = 1u;
+                if (rem > 0) {
+                    diff = lds32u(base + ms + k) ^ lds32u(base + mc + k);
+                    if (rem < 4) diff = (diff & ((1u << (8 * rem)) - 1u)) | (1u << (8 * rem));
+                }
                 const u32 mm = __ballot_sync(0xFFFFFFFFu, diff != 0);
                 if (mm) {
                     const u32 fl = __ffs(mm) - 1;
                     const u32 d = __shfl_sync(0xFFFFFFFFu, diff, fl);
-                    const u32 inb = __shfl_sync(0xFFFFFFFFu, (u32)in, fl);
-                    len += 4 * fl + (inb ? ((u32)__ffs(d) - 1) >> 3 : 0u);
+                    len += 4 * fl + (((u32)__ffs(d) - 1) >> 3);
                     break;
                 }
                 len += 128;
             }
             const u32 ll = ms - anchor;
-            warp_copy(lit + nlit, s + anchor, ll, lane);
-            if (lane == 0) seq[nseq] = (u64)ll | ((u64)len << 18) | ((u64)(ms - mc) << 36);
+            if (lane == 0) seqq[nseq] = (u64)ll | ((u64)len << 18) | ((u64)(ms - mc) << 36);
             nseq++;
             nlit += ll;
             anchor = pos = ms + len;
-            if (nseq == B.seq_cap) break;
+            if (nseq == qcap) break;
         }
-        warp_copy_to_end(lit + nlit, s + anchor, n - anchor, lane);
-        nlit += n - anchor;
-        ck.n_seq = nseq; ck.lit_size = nlit;
-        if (lane == 0) B.chunks[i] = ck;
+        const u32 tail = q1 - anchor;
+        if (lane == 0) { misc[warp] = nseq; misc[8 + warp] = nlit + tail; misc[16 + warp] = tail; }
+        __syncthreads();
+        // ---- literal runs of this part, from shared memory to their final place
+        u32 lbase = 0, carry = 0;                                // literal bytes before the part; literals pending in front of it
+        for (u32 q = 0; q < warp; q++) {
+            lbase += misc[8 + q];
+            carry = misc[q] ? misc[16 + q] : carry + misc[8 + q];
+        }
+        u8* const lit = B.dst + B.dst_off[i] + kzg_enc_header_size(n) + 6 + lbase;
+        u32 spos = q0, dpos = 0;
+        for (u32 b = 0; b < nseq; b += 32) {
+            const bool have = b + lane < nseq;
+            const u64 rec = have ? seqq[b + lane] : 0ull;
+            const u32 ll = (u32)rec & 0x3FFFFu, ml = (u32)(rec >> 18) & 0x3FFFFu;
+            const u32 sa = warp_incl_sum(ll + ml, lane), sl = warp_incl_sum(ll, lane);
+            const u32 my_src = spos + sa - ll - ml, my_dst = dpos + sl - ll;
+            // short runs: every lane copies its own; long ones: the warp together
+            const u32 longm = __ballot_sync(0xFFFFFFFFu, ll >= 64);
+            if (ll < 64) for (u32 t = 0; t < ll; t++) lit[my_dst + t] = (u8)lds8(base + my_src + t);
+            for (u32 mm = longm; mm; mm &= mm - 1) {
+                const u32 j = __ffs(mm) - 1;
+                warp_copy_from_smem(lit + __shfl_sync(0xFFFFFFFFu, my_dst, j), base + __shfl_sync(0xFFFFFFFFu, my_src, j),
+                                    __shfl_sync(0xFFFFFFFFu, ll, j), lane);
+            }
+            spos += __shfl_sync(0xFFFFFFFFu, sa, 31);
+            dpos += __shfl_sync(0xFFFFFFFFu, sl, 31);
+        }
+        warp_copy_from_smem(lit + dpos, base + q1 - tail, tail, lane);
+        // literals pending in front of the part belong to its first sequence
+        if (lane == 0 && nseq && carry) seqq[0] += carry;
+        if (threadIdx.x == 0) {
+            KzgEncChunk ck;
+            ck.lit_size = 0;
+            for (u32 q = 0; q < KZG_ENC_WARPS; q++) { ck.n_seq[q] = misc[q]; ck.lit_size += misc[8 + q]; }
+            ck.state = 0; ck.total = 0; ck.pad = 0;
+            B.chunks[i] = ck;
+        }
     }
 }
 
-__global__ void __launch_bounds__(128) kzg_enc_encode_kernel(KzgEncBatch B) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B.n) kzg_enc_stage_encode(B, i);
+// encode stage: one warp per chunk.  Shared memory per warp: the three FSE tables' lookups go to global memory
+// (constant, cached); 3 x 32 words of chain results and a 640-byte bit staging area live here.
+#define KZG_ENC_EWARPS 4
+#define KZG_ENC_STAGE_WORDS 96       // 32 sequences x at most 66 bits = 2112 bits < 96 words, plus the carried partial byte
+__global__ void __launch_bounds__(KZG_ENC_EWARPS * 32) kzg_enc_encode_kernel(KzgEncBatch B) {
+    using namespace kzg_encd;
+    __shared__ u32 s_chain[KZG_ENC_EWARPS][3][32];
+    __shared__ u32 s_bits[KZG_ENC_EWARPS][KZG_ENC_STAGE_WORDS];
+    __shared__ KzgEncTables s_tab;
+    __shared__ uint2 s_delta[36 + 53 + 32];        // {deltaNbBits, deltaFindState} of LL | ML | OF symbols
+    __shared__ u32 s_syms[KZG_ENC_EWARPS][100];    // per warp: codes of the batch (3 x 32), final states (3)
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 k = threadIdx.x; k < sizeof(KzgEncTables) / 4; k += blockDim.x) reinterpret_cast<u32*>(&s_tab)[k] = reinterpret_cast<const u32*>(B.tab)[k];
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < 36 + 53 + 32; k += blockDim.x)
+        s_delta[k] = k < 36 ? make_uint2(s_tab.dnb_ll[k], (u32)s_tab.dfs_ll[k])
+                            : (k < 89 ? make_uint2(s_tab.dnb_ml[k - 36], (u32)s_tab.dfs_ml[k - 36]) : make_uint2(s_tab.dnb_of[k - 89], (u32)s_tab.dfs_of[k - 89]));
+    __syncthreads();
+    u32* syms = s_syms[warp];
+    const KzgEncTables* T = &s_tab;
+    u32* chain = &s_chain[warp][0][0];
+    u32* bits = s_bits[warp];
+    for (;;) {
+        u32 i = 0;
+        if (lane == 0) i = atomicAdd(&B.tickets[2], 1u);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= B.n) break;
+        const KzgEncChunk ck = B.chunks[i];
+        u32 nseq = 0;
+#pragma unroll
+        for (int q = 0; q < KZG_ENC_WARPS; q++) nseq += ck.n_seq[q];
+        const u32 qcap = B.seq_cap / KZG_ENC_WARPS;
+        u8 *blk = nullptr, *limit = nullptr, *p = nullptr;
+        if (lane == 0) p = kzg_enc_block_prologue(B, i, nseq, blk, limit);
+        p = reinterpret_cast<u8*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)p, 0));
+        if (!p) continue;
+        blk = reinterpret_cast<u8*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)blk, 0));
+        limit = reinterpret_cast<u8*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)limit, 0));
+        u64* seq = B.seq + (size_t)i * B.seq_cap;
+        // ---- forward: offset values with repeat codes.  Loads and stores are coalesced, the history walk runs on
+        // every lane redundantly (uniform control flow, no divergence) over shuffled records.
+        {
+            u32 r0 = 1, r1 = 4, r2 = 8;
+#pragma unroll 1
+            for (int q = 0; q < KZG_ENC_WARPS; q++) {
+                const u32 nq = B.chunks[i].n_seq[q];
+                u64* sq = seq + (size_t)q * qcap;
+                for (u32 b = 0; b < nq; b += 32) {
+                    const bool have = b + lane < nq;
+                    const u64 rec = have ? sq[b + lane] : 0ull;
+                    const u32 cnt = min(32u, nq - b);
+                    u32 mine = 0;
+                    for (u32 j = 0; j < cnt; j++) {
+                        const u64 rj = __shfl_sync(0xFFFFFFFFu, rec, j);
+                        const u32 ob = kzg_enc_offset_value((u32)rj & 0x3FFFFu, (u32)(rj >> 36) & 0x3FFFFu, r0, r1, r2);
+                        if (j == lane) mine = ob;
+                    }
+                    if (have) sq[b + lane] = (rec & 0xFFFFFFFFFull) | ((u64)mine << 36);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- backward: batches of at most 32 sequences inside one part, lane j <-> sequence hi - 1 - j (the order
+        // they are written in)
+        u32 stLL = 0, stML = 0, stOF = 0;          // current states (kept on every lane)
+        u32 carry_bits = 0, carry_n = 0;            // bits of the last, incomplete byte
+        u8* out = p;
+        bool ovf = false, first = true;
+#pragma unroll 1
+        for (int q = KZG_ENC_WARPS - 1; q >= 0 && !ovf; q--) {
+            const u64* sq = seq + (size_t)q * qcap;
+            for (u32 hi = B.chunks[i].n_seq[q]; hi > 0;) {
+                const u32 cnt = min(32u, hi);
+                const bool have = lane < cnt;
+                const u64 rec = have ? sq[hi - 1 - lane] : 0ull;
+                const u32 ll = (u32)rec & 0x3FFFFu, mlb = have ? ((u32)(rec >> 18) & 0x3FFFFu) - 3u : 0u, ob = have ? (u32)(rec >> 36) & 0x3FFFFu : 1u;
+                const u32 cl = kzg_enc_ll_code(T, ll), cm = kzg_enc_ml_code(T, mlb), co = (u32)kzg_highbit(ob);
+                // the three state chains on lanes 0 (LL), 1 (ML), 2 (OF) over the codes parked in shared memory;
+                // results: value bits | nb << 16 per sequence
+                syms[lane] = cl; syms[32 + lane] = cm; syms[64 + lane] = co;
+                __syncwarp();
+                if (lane < 3) {
+                    const u16* st = lane == 0 ? s_tab.st_ll : (lane == 1 ? s_tab.st_ml : s_tab.st_of);
+                    const uint2* dd = s_delta + (lane == 0 ? 0 : (lane == 1 ? 36 : 89));
+                    const u32* my = syms + 32 * lane;
+                    u32* res = chain + 32 * lane;
+                    u32 value = lane == 0 ? stLL : (lane == 1 ? stML : stOF);
+                    u32 j = 0;
+                    if (first) {                               // the very last sequence initialises the states
+                        const uint2 d = dd[my[0]];
+                        const u32 nb = (d.x + (1u << 15)) >> 16;
+                        value = st[(i32)(((nb << 16) - d.x) >> nb) + (i32)d.y];
+                        res[0] = 0;
+                        j = 1;
+                    }
+                    for (; j < cnt; j++) {
+                        const uint2 d = dd[my[j]];
+                        const u32 nb = (value + d.x) >> 16;
+                        res[j] = (value & ((1u << nb) - 1u)) | (nb << 16);
+                        value = st[(i32)(value >> nb) + (i32)d.y];
+                    }
+                    syms[96 + lane] = value;
+                }
+                __syncwarp();
+                stLL = syms[96]; stML = syms[97]; stOF = syms[98];
+                first = false;
+                __syncwarp();
+                // this lane's fields, in stream order: OF state, ML state, LL state, LL extra, ML extra, OF extra
+                u32 fv[6], fn[6];
+                {
+                    const u32 eL = chain[lane], eM = chain[32 + lane], eO = chain[64 + lane];
+                    fv[0] = eO & 0xFFFFu; fn[0] = eO >> 16;
+                    fv[1] = eM & 0xFFFFu; fn[1] = eM >> 16;
+                    fv[2] = eL & 0xFFFFu; fn[2] = eL >> 16;
+                    fn[3] = T->ll_tab[cl] >> 24; fv[3] = ll & ((1u << fn[3]) - 1u);
+                    fn[4] = T->ml_tab[cm] >> 24; fv[4] = mlb & ((1u << fn[4]) - 1u);
+                    fn[5] = co; fv[5] = ob & ((1u << co) - 1u);
+                    if (!have) { fn[0] = fn[1] = fn[2] = fn[3] = fn[4] = fn[5] = 0; }
+                }
+                const u32 mylen = fn[0] + fn[1] + fn[2] + fn[3] + fn[4] + fn[5];
+                const u32 incl = warp_incl_sum(mylen, lane);
+                const u32 total = carry_n + __shfl_sync(0xFFFFFFFFu, incl, 31);
+                for (u32 k = lane; k < KZG_ENC_STAGE_WORDS; k += 32) bits[k] = k == 0 ? carry_bits : 0u;
+                __syncwarp();
+                u32 bp = carry_n + incl - mylen;
+#pragma unroll
+                for (int f = 0; f < 6; f++) {
+                    if (fn[f]) {
+                        const u64 v = (u64)fv[f] << (bp & 31u);
+                        atomicOr(&bits[bp >> 5], (u32)v);
+                        if ((u32)(v >> 32)) atomicOr(&bits[(bp >> 5) + 1], (u32)(v >> 32));
+                    }
+                    bp += fn[f];
+                }
+                __syncwarp();
+                // whole bytes leave; the incomplete last byte is carried into the next batch
+                const u32 nbytes = total >> 3;
+                if (out + nbytes > limit) { ovf = true; break; }
+                for (u32 k = lane; k < nbytes; k += 32) out[k] = (u8)(bits[k >> 2] >> (8 * (k & 3)));
+                carry_n = total & 7u;
+                carry_bits = carry_n ? (bits[nbytes >> 2] >> (8 * (nbytes & 3))) & 0xFFu : 0u;
+                out += nbytes;
+                hi -= cnt;
+                __syncwarp();
+            }
+        }
+        if (ovf) continue;                                       // not smaller than raw: stays ST_RAW
+        if (lane == 0) {
+            KzgBitW w;
+            w.acc = carry_bits; w.nbits = carry_n; w.p = out; w.end = limit; w.ovf = false;
+            kzg_bw_add(w, stML, 6);
+            kzg_bw_add(w, stOF, 5);
+            kzg_bw_add(w, stLL, 6);
+            kzg_bw_add(w, 1, 1);                                 // end mark
+            kzg_bw_flush(w);
+            if (w.nbits) { if (w.p < w.end) *w.p = (u8)w.acc; else w.ovf = true; w.p++; }
+            if (!w.ovf && w.p < limit) kzg_enc_block_epilogue(B, i, blk, w.p);
+        }
+        __syncwarp();
+    }
 }
 
 // finish stage: raw-block fallback, checksum trailer, sizes.  One warp per chunk.

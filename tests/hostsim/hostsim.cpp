@@ -141,7 +141,7 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
     u64 max_chunk = 0;
     for (u64 i = 0; i < n; i++) if (src_size[i] > max_chunk) max_chunk = src_size[i];
     if (max_chunk > KZG_BLOCK_MAX) max_chunk = KZG_BLOCK_MAX;
-    const u32 seq_cap = (u32)(max_chunk / 8 + 64);
+    const u32 seq_cap = KZG_ENC_WARPS * (u32)(max_chunk / 6 + 64);     // everything goes to the first part's region
     std::vector<u64> seq((size_t)n * seq_cap);
     std::vector<KzgEncChunk> chunks(n);
     KzgEncBatch B;
@@ -149,10 +149,11 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
     B.src = src; B.src_off = src_off; B.src_size = src_size; B.dst = dst; B.dst_off = dst_off; B.dst_cap = dst_cap;
     B.status = status; B.out_size = out_size; B.n = (u32)n; B.flags = (u32)flags;
     B.seq = seq.data(); B.seq_cap = seq_cap; B.chunks = chunks.data(); B.tab = &tables;
-    std::vector<u32> table(1u << KZG_ENC_HASH_LOG);
+    std::vector<u32> table(1u << 12);
     for (u32 i = 0; i < n; i++) {
         KzgEncChunk& ck = chunks[i];
-        ck.n_seq = 0; ck.lit_size = 0; ck.state = 0; ck.total = 0;
+        for (u32 q = 0; q < KZG_ENC_WARPS; q++) ck.n_seq[q] = 0;
+        ck.lit_size = 0; ck.state = 0; ck.total = 0; ck.pad = 0;
         const u32 len = (u32)src_size[i];
         if (src_size[i] > KZG_BLOCK_MAX || dst_cap[i] < kzg_enc_bound(len) || len < 64) continue;
         const u8* s = src + src_off[i];
@@ -161,8 +162,8 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
         std::fill(table.begin(), table.end(), 0xFFFFFFFFu);
         const u32 limit = len - 12;
         u32 pos = 0, anchor = 0;
-        while (pos < limit && ck.n_seq < seq_cap) {
-            const u32 v = kzg_rd32(s + pos), h = (v * 2654435761u) >> (32 - KZG_ENC_HASH_LOG);
+        while (pos < limit && ck.n_seq[0] < seq_cap / KZG_ENC_WARPS) {
+            const u32 v = kzg_rd32(s + pos), h = (v * 2654435761u) >> (32 - 12);
             const u32 cand = table[h];
             table[h] = pos;
             if (cand == 0xFFFFFFFFu || kzg_rd32(s + cand) != v) { pos++; continue; }
@@ -170,7 +171,7 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
             while (pos + ml < len && s[cand + ml] == s[pos + ml]) ml++;
             const u32 ll = pos - anchor;
             memcpy(lit + ck.lit_size, s + anchor, ll);
-            rec[ck.n_seq++] = (u64)ll | ((u64)ml << 18) | ((u64)(pos - cand) << 36);
+            rec[ck.n_seq[0]++] = (u64)ll | ((u64)ml << 18) | ((u64)(pos - cand) << 36);
             ck.lit_size += ll;
             anchor = pos = pos + ml;
         }
