@@ -153,6 +153,25 @@ size_t kzg_DCtx_loadDictionary(kzg_DCtx* dctx, const void* dict, size_t dictSize
  * (ZstdDecompressor.jvm.kt:38, ZstdDecompressor.native.kt:72). */
 size_t kzg_decompressStream(kzg_DCtx* dctx, kzg_outBuffer* output, kzg_inBuffer* input);
 
+/* Compress side of the shim, on top of the batch frame writer: the libzstd functions
+ * behind ZstdWrapper.createCompressor / freeCompressor / setParameter / loadCompressorDictionary / compressStream
+ * (Wrapper.cpp:10-56,75-121; ZstdCompressor.jvm.kt:10-42, ZstdCompressor.native.kt:28-80).
+ *   kzg_createCCtx            ZSTD_createCCtx (NULL if no GPU)
+ *   kzg_CCtx_setParameter     ZSTD_CCtx_setParameter: 201 (checksumFlag) is honoured; 100-107, 200, 202 are accepted
+ *                             (one fixed parse, content size always written); others: parameter_unsupported (40)
+ *   kzg_CCtx_loadDictionary   raw-content dictionaries are accepted (and not referenced); formatted ones: 40
+ *   kzg_compressStream2       ZSTD_compressStream2; end_op 0 = ZSTD_e_continue, 1 = flush, 2 = ZSTD_e_end.  All input
+ *                             is consumed; the result is the number of bytes still to be flushed (0 = done), which
+ *                             is what `output.insufficient = input.hasData || (finish && result != 0)` needs.
+ * The stream is written as independent 64 KiB frames (not one long frame): any zstd decoder reads the
+ * concatenation, and the batch decoder reads it in bulk. */
+typedef struct kzg_CCtx kzg_CCtx;
+kzg_CCtx* kzg_createCCtx(void);
+size_t kzg_freeCCtx(kzg_CCtx* cctx);
+size_t kzg_CCtx_setParameter(kzg_CCtx* cctx, int param, int value);
+size_t kzg_CCtx_loadDictionary(kzg_CCtx* cctx, const void* dict, size_t dictSize);
+size_t kzg_compressStream2(kzg_CCtx* cctx, kzg_outBuffer* output, kzg_inBuffer* input, int end_op);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ EXPORTS = [
     "kzg_last_batch_stats", "kzg_ctx_set_dictionary", "kzg_ctx_set_profiling", "kzg_last_stage_ms", "kzg_createDCtx", "kzg_freeDCtx", "kzg_DCtx_loadDictionary", "kzg_decompressStream",
     "kzg_enc_create", "kzg_enc_destroy", "kzg_compress_bound", "kzg_compress_batch_device", "kzg_enc_finish",
     "kzg_compress_batch_host", "kzg_enc_set_profiling", "kzg_enc_last_stage_ms",
+    "kzg_createCCtx", "kzg_freeCCtx", "kzg_CCtx_setParameter", "kzg_CCtx_loadDictionary", "kzg_compressStream2",
 ]
 
 _lib = None
@@ -100,6 +101,15 @@ def lib() -> ctypes.CDLL:
     L.kzg_enc_set_profiling.restype = c_int
     L.kzg_enc_last_stage_ms.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
     L.kzg_enc_last_stage_ms.restype = c_int
+    L.kzg_createCCtx.restype = c_void_p
+    L.kzg_freeCCtx.argtypes = [c_void_p]
+    L.kzg_freeCCtx.restype = c_size_t
+    L.kzg_CCtx_setParameter.argtypes = [c_void_p, c_int, c_int]
+    L.kzg_CCtx_setParameter.restype = c_size_t
+    L.kzg_CCtx_loadDictionary.argtypes = [c_void_p, c_void_p, c_size_t]
+    L.kzg_CCtx_loadDictionary.restype = c_size_t
+    L.kzg_compressStream2.argtypes = [c_void_p, POINTER(OutBuffer), POINTER(InBuffer), c_int]
+    L.kzg_compressStream2.restype = c_size_t
     if hasattr(L, "kzg_createDCtx"):
         L.kzg_createDCtx.restype = c_void_p
         L.kzg_freeDCtx.argtypes = [c_void_p]

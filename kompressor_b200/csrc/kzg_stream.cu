@@ -391,3 +391,130 @@ extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_i
     if (frames_done || delivered) return 0;               // frame boundary, everything flushed
     return 9;                                             // idle at a frame start (libzstd: header + block header hint)
 }
+
+// ------------------------------------------------------------------------------------------------
+// Compress side of the shim: the libzstd functions behind
+// Java_..._ZstdWrapper_createCompressor / freeCompressor / setParameter / loadCompressorDictionary / compressStream
+// (Wrapper.cpp:10-56,75-121; Kotlin: ZstdCompressor.jvm.kt:10-42), on top of the batch frame writer.
+// The stream is cut into chunks of 64 KiB and every chunk becomes one independent frame, so what this
+// compressor writes is what the batch decoder reads fastest; any zstd decoder accepts the concatenation.
+// In transform(ByteArray) the first call offers the whole input with finish = true (SliceTransform.kt:33-45):
+// all chunks are compressed as one GPU batch and the output is drained over the following calls.
+namespace {
+std::mutex g_enc_mu;
+kzg_enc* g_enc = nullptr;
+const size_t kChunk = 65536;
+}  // namespace
+
+struct kzg_CCtx {
+    std::vector<u8> in;              // input not yet compressed (less than one chunk between calls)
+    Arena out;                       // frames not yet handed to the caller: out.p[out_pos, out_size)
+    size_t out_size = 0, out_pos = 0;
+    bool checksum = false;
+    bool wrote_frame = false;        // since the last completed e_end
+    std::vector<uint64_t> off, size, doff, cap, osize;
+    std::vector<uint32_t> status;
+};
+
+extern "C" kzg_CCtx* kzg_createCCtx(void) {
+    {
+        std::lock_guard<std::mutex> lock(g_enc_mu);
+        if (!g_enc && kzg_enc_create(&g_enc, -1) != 0) return nullptr;      // no GPU: no compressor
+    }
+    return new (std::nothrow) kzg_CCtx();
+}
+
+extern "C" size_t kzg_freeCCtx(kzg_CCtx* c) {
+    if (c) g_pool.release(c->out);
+    delete c;
+    return 0;
+}
+
+extern "C" size_t kzg_CCtx_setParameter(kzg_CCtx* c, int param, int value) {
+    if (!c) return err(KZG_E_GENERIC);
+    if (param == 201) { c->checksum = value != 0; return 0; }               // ZSTD_c_checksumFlag
+    // compression level, window / hash / chain / search logs, minMatch, targetLength, strategy, content-size and
+    // dictionary-ID flags: accepted; the frame writer has one fixed parse and always writes the content size
+    if ((param >= 100 && param <= 107) || param == 200 || param == 202) return 0;
+    return err(40 /* parameter_unsupported */);
+}
+
+extern "C" size_t kzg_CCtx_loadDictionary(kzg_CCtx* c, const void* dict, size_t n) {
+    if (!c) return err(KZG_E_GENERIC);
+    if (!dict || n == 0) return 0;
+    // A raw-content dictionary only adds history: frames that do not reference it stay valid for a decoder that has
+    // it loaded.  A formatted one would also change the decoder's initial repeat offsets, which this writer relies on.
+    if (n >= 8 && kzg_rd32((const u8*)dict) == KZG_DICT_MAGIC) return err(40 /* parameter_unsupported */);
+    return 0;
+}
+
+// Compresses the first `nbytes` of c->in (whole chunks, plus a short last one) and appends the frames to c->out.
+static size_t compress_buffered(kzg_CCtx* c, size_t nbytes) {
+    const size_t n = nbytes ? (nbytes + kChunk - 1) / kChunk : 1;            // nbytes == 0: the empty frame
+    try {
+        c->off.resize(n); c->size.resize(n); c->doff.resize(n); c->cap.resize(n); c->osize.resize(n); c->status.resize(n);
+    } catch (const std::bad_alloc&) { return err(KZG_E_MEMORY); }
+    uint64_t total_cap = 0;
+    for (size_t i = 0; i < n; i++) {
+        c->off[i] = i * kChunk;
+        c->size[i] = nbytes - i * kChunk < kChunk ? nbytes - i * kChunk : kChunk;
+        c->cap[i] = (kzg_compress_bound((size_t)c->size[i]) + 15) & ~(size_t)15;
+        c->doff[i] = total_cap;
+        total_cap += c->cap[i];
+    }
+    const size_t pending = c->out_size - c->out_pos;
+    Arena a = g_pool.acquire(pending + total_cap + 64);
+    if (!a.p) return err(KZG_E_MEMORY);
+    if (pending) memcpy(a.p, c->out.p + c->out_pos, pending);
+    g_pool.release(c->out);
+    c->out = a;
+    c->out_pos = 0;
+    c->out_size = pending;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(g_enc_mu);
+        rc = kzg_compress_batch_host(g_enc, c->in.data(), c->off.data(), c->size.data(), c->out.p + pending, c->doff.data(),
+                                     c->cap.data(), n, c->checksum ? KZG_COMPRESS_CHECKSUM : 0, c->status.data(), c->osize.data());
+    }
+    if (rc < 0) return err((u32)(-rc));
+    size_t w = pending;
+    for (size_t i = 0; i < n; i++) {
+        if (c->status[i]) return err(c->status[i]);
+        if (w != pending + c->doff[i]) memmove(c->out.p + w, c->out.p + pending + c->doff[i], c->osize[i]);
+        w += c->osize[i];
+    }
+    c->out_size = w;
+    c->wrote_frame = true;
+    return 0;
+}
+
+extern "C" size_t kzg_compressStream2(kzg_CCtx* c, kzg_outBuffer* output, kzg_inBuffer* input, int end_op) {
+    if (!c || !output || !input) return err(KZG_E_GENERIC);
+    if (input->pos > input->size || output->pos > output->size) return err(KZG_E_SRCSIZE_WRONG);
+    if (end_op < 0 || end_op > 2) return err(42 /* parameter_outOfBound */);
+    const size_t avail = input->size - input->pos;
+    if (avail) {
+        try { c->in.insert(c->in.end(), (const u8*)input->src + input->pos, (const u8*)input->src + input->size); }
+        catch (const std::bad_alloc&) { return err(KZG_E_MEMORY); }
+        input->pos = input->size;
+    }
+    // whole chunks are compressed as soon as they are buffered; flush / end also take the short rest
+    size_t take = end_op == 0 ? c->in.size() / kChunk * kChunk : c->in.size();
+    if (take || (end_op == 2 && !c->wrote_frame && c->out_size == c->out_pos)) {
+        const size_t e = compress_buffered(c, take);
+        if (kzg_isError(e)) return e;
+        c->in.erase(c->in.begin(), c->in.begin() + take);
+    }
+    const size_t have = c->out_size - c->out_pos, room = output->size - output->pos;
+    const size_t n = have < room ? have : room;
+    if (n) memcpy((u8*)output->dst + output->pos, c->out.p + c->out_pos, n);
+    output->pos += n;
+    c->out_pos += n;
+    const size_t pending = c->out_size - c->out_pos;
+    if (pending == 0) {
+        c->out_pos = c->out_size = 0;
+        if (c->out.cap > (1u << 20)) g_pool.release(c->out);
+        if (end_op == 2) c->wrote_frame = false;               // the stream is complete: the next call starts a new one
+    }
+    return pending;
+}

@@ -68,9 +68,55 @@ class ZstdDecompressorImpl(SliceTransform):
         output.insufficient = output.isFull and result != 0
 
 
+class ZstdCompressorImpl(SliceTransform):
+    """ZstdCompressor.jvm.kt:10-42 on top of the kzg frame writer (compress side of the shim).  The stream is written
+    as independent 64 KiB frames; `compressionLevel` is accepted and has no effect (one fixed parse)."""
+
+    def __init__(self, compressionLevel: int = 3, dictionary: bytes | None = None):
+        self._L = lib()
+        self.cctx = self._L.kzg_createCCtx()
+        if not self.cctx:
+            raise IllegalStateException("Failed allocating zstd cctx (kzg needs a CUDA device; there is no CPU fallback)")
+        self._L.kzg_CCtx_setParameter(self.cctx, 100, compressionLevel)        # ZstdParameter.compressionLevel
+        if dictionary is not None:
+            buf = (ctypes.c_char * len(dictionary)).from_buffer_copy(dictionary)
+            checkErrorResult(self._L.kzg_CCtx_loadDictionary(self.cctx, buf, len(dictionary)))
+
+    def setParameter(self, parameter: int, value: int) -> None:                # ZstdWrapper.setParameter
+        checkErrorResult(self._L.kzg_CCtx_setParameter(self.cctx, parameter, value))
+
+    def close(self) -> None:
+        if getattr(self, "cctx", None):
+            self._L.kzg_freeCCtx(self.cctx)
+            self.cctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform(self, input: ByteArraySlice, output: ByteArraySlice, finish: bool) -> None:  # noqa: A002
+        in_arr = (ctypes.c_char * max(1, len(input.data))).from_buffer(input.data) if len(input.data) else None
+        out_arr = (ctypes.c_char * max(1, len(output.data))).from_buffer(output.data) if len(output.data) else None
+        inb = InBuffer(ctypes.addressof(in_arr) if in_arr is not None else None, input.writeStart, input.readStart)
+        outb = OutBuffer(ctypes.addressof(out_arr) if out_arr is not None else None, output.writeLimit, output.writeStart)
+        result = self._L.kzg_compressStream2(self.cctx, ctypes.byref(outb), ctypes.byref(inb), 2 if finish else 0)
+        input.readStart = inb.pos
+        output.writeStart = outb.pos
+        del in_arr, out_arr
+        checkErrorResult(result)
+        output.insufficient = input.hasData or (finish and result != 0)        # ZstdCompressor.jvm.kt:40
+
+
+def ZstdCompressor(compressionLevel: int = 3, dictionary: bytes | None = None) -> SliceTransform:
+    """public expect fun ZstdCompressor(compressionLevel: Int = 3, dictionary: ByteArray? = null): SliceTransform"""
+    return ZstdCompressorImpl(compressionLevel=compressionLevel, dictionary=dictionary)
+
+
 def ZstdDecompressor(dictionary: bytes | None = None) -> SliceTransform:
     """public expect fun ZstdDecompressor(dictionary: ByteArray? = null): SliceTransform"""
     return ZstdDecompressorImpl(dictionary=dictionary)
 
 
-__all__ = ["ZstdDecompressor", "ZstdDecompressorImpl", "IllegalStateException", "checkErrorResult", "KzgError"]
+__all__ = ["ZstdCompressor", "ZstdCompressorImpl", "ZstdDecompressor", "ZstdDecompressorImpl", "IllegalStateException", "checkErrorResult", "KzgError"]

@@ -176,3 +176,44 @@ def test_many_handles_in_parallel(api, libzstd):
             assert results[i] is not None and results[i].startswith("error"), (i, results[i])
         else:
             assert results[i] == "ok", (i, results[i])
+
+
+# ---------------------------------------------------------------- the reference's round trips with this build's compressor
+def test_roundtrip_with_own_compressor(api, libzstd):   # ZstdTest.kt:19-38 (tinySample, sampleRoundtrip, ...KotlinxIoSource)
+    import corpus
+    core, io, zstd = api
+    tiny = np.random.default_rng(11).integers(0, 256, 9000, dtype=np.uint8).tobytes()
+    text = bytes(corpus.generate("logs", 12, 1024 * 1024 + 3))
+    rnd = np.random.default_rng(13).integers(0, 256, 1024 * 1024 + 3, dtype=np.uint8).tobytes()
+    for data in (tiny, text, rnd, b"", b"x"):
+        compressed = core.transform(zstd.ZstdCompressor(compressionLevel=3), data)
+        assert core.transform(zstd.ZstdDecompressor(), compressed) == data
+        out, err = libzstd.decompress_oneshot(compressed, len(data) + 64)       # and the real libzstd reads it
+        assert err == 0 and out == data
+    assert len(core.transform(zstd.ZstdCompressor(), text)) < len(text) // 2
+    source = io.pipe(io.pipe(text, zstd.ZstdCompressor(compressionLevel=3)), zstd.ZstdDecompressor())
+    assert source.readByteArray() == text
+
+
+def test_compressor_parameters_and_dictionaries(api, libzstd):
+    core, _, zstd = api
+    data = b"this is some data to compress using a dictionary" * 50
+    c = zstd.ZstdCompressor()
+    c.setParameter(201, 1)                               # ZSTD_c_checksumFlag
+    framed = core.transform(c, data)
+    assert framed[4] & 4                                 # Content_Checksum flag of the frame header descriptor
+    assert core.transform(zstd.ZstdDecompressor(), framed) == data
+    with pytest.raises(zstd.IllegalStateException) as ei:
+        c.setParameter(9999, 1)
+    assert ei.value.code == 40
+    # a raw-content dictionary is accepted (the frames do not reference it, so they decode with or without it)
+    raw_dict = b"this is a test dictionary"
+    compressed = core.transform(zstd.ZstdCompressor(dictionary=raw_dict), data)
+    assert core.transform(zstd.ZstdDecompressor(dictionary=raw_dict), compressed) == data
+    assert core.transform(zstd.ZstdDecompressor(), compressed) == data
+    # a formatted dictionary is refused instead of silently producing frames that need other repeat offsets
+    import corpus
+    trained = libzstd.train_dictionary([bytes(corpus.generate("logs", 300 + i, 1500)) for i in range(200)], 8192)
+    with pytest.raises(zstd.IllegalStateException) as ei:
+        zstd.ZstdCompressor(dictionary=trained)
+    assert ei.value.code == 40
