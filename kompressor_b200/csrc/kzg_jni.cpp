@@ -10,9 +10,14 @@
 //   Java_com_ensody_kompressor_zstd_ZstdWrapper_getErrorName                Wrapper.cpp:189-196
 //   JNI_OnLoad / JNI_OnUnload (field IDs of ByteArraySlice)                 jni/common/src/DefaultLoad.cpp:11-37,
 //                                                                           jni/common/src/SliceClass.cpp:4-7
+//   Java_com_ensody_kompressor_zstd_ZstdWrapper_createCompressor / freeCompressor   Wrapper.cpp:10-28
+//   Java_com_ensody_kompressor_zstd_ZstdWrapper_setParameter                        Wrapper.cpp:30-40
+//   Java_com_ensody_kompressor_zstd_ZstdWrapper_loadCompressorDictionary            Wrapper.cpp:42-56
+//   Java_com_ensody_kompressor_zstd_ZstdWrapper_compressStream                      Wrapper.cpp:75-121
 // The Kotlin declarations they bind are ZstdWrapper.kt:24-60 (a Kotlin `object`, hence the jobject
-// receiver).  The compress-side symbols stay with the real libzstd-jni: INTEGRATION.md shows how the
-// two libraries are loaded side by side.
+// receiver).  With the compress-side symbols (on top of the batch frame writer) the library exports
+// everything libzstd-jni.so does; a build that keeps libzstd for compression simply does not re-point
+// those five (INTEGRATION.md shows the two libraries loaded side by side).
 //
 // Difference from the reference on purpose: array access is limited to
 // the slice ranges (Get/SetByteArrayRegion) instead of Get/ReleaseByteArrayElements on the whole arrays,
@@ -81,6 +86,52 @@ JNIEXPORT jlong JNICALL Java_com_ensody_kompressor_zstd_ZstdWrapper_decompressSt
     kzg_inBuffer ib = { in.data(), static_cast<size_t>(in_n), 0 };
     kzg_outBuffer ob = { out.data(), static_cast<size_t>(out_n), 0 };
     const size_t result = kzg_decompressStream(reinterpret_cast<kzg_DCtx*>(dctx), &ob, &ib);
+    if (ob.pos > 0) {
+        env->SetByteArrayRegion(outputByteArray, outputStart, static_cast<jsize>(ob.pos), out.data());
+        if (env->ExceptionCheck()) return kGenericError;
+    }
+    env->SetIntField(inputSlice, g_readStart, inputStart + static_cast<jint>(ib.pos));
+    env->SetIntField(outputSlice, g_writeStart, outputStart + static_cast<jint>(ob.pos));
+    return static_cast<jlong>(result);
+}
+
+JNIEXPORT jlong JNICALL Java_com_ensody_kompressor_zstd_ZstdWrapper_createCompressor(JNIEnv*, jobject) {
+    return reinterpret_cast<jlong>(kzg_createCCtx());         // 0 if no GPU: Kotlin throws "Failed allocating zstd cctx"
+}
+
+JNIEXPORT void JNICALL Java_com_ensody_kompressor_zstd_ZstdWrapper_freeCompressor(JNIEnv*, jobject, jlong cctx) {
+    kzg_freeCCtx(reinterpret_cast<kzg_CCtx*>(cctx));
+}
+
+JNIEXPORT jlong JNICALL Java_com_ensody_kompressor_zstd_ZstdWrapper_setParameter(JNIEnv*, jobject, jlong cctx, jint parameter, jint value) {
+    return static_cast<jlong>(kzg_CCtx_setParameter(reinterpret_cast<kzg_CCtx*>(cctx), parameter, value));
+}
+
+JNIEXPORT jlong JNICALL Java_com_ensody_kompressor_zstd_ZstdWrapper_loadCompressorDictionary(JNIEnv* env, jobject, jlong cctx,
+                                                                                             jbyteArray dictionary) {
+    const jsize n = env->GetArrayLength(dictionary);
+    std::vector<jbyte> buf(static_cast<size_t>(n > 0 ? n : 0));
+    if (n > 0) {
+        env->GetByteArrayRegion(dictionary, 0, n, buf.data());
+        if (env->ExceptionCheck()) return kGenericError;
+    }
+    return static_cast<jlong>(kzg_CCtx_loadDictionary(reinterpret_cast<kzg_CCtx*>(cctx), buf.data(), buf.size()));
+}
+
+JNIEXPORT jlong JNICALL Java_com_ensody_kompressor_zstd_ZstdWrapper_compressStream(
+        JNIEnv* env, jobject, jlong cctx, jobject inputSlice, jbyteArray inputByteArray, jint inputStart, jint inputEndExclusive,
+        jobject outputSlice, jbyteArray outputByteArray, jint outputStart, jint outputEndExclusive, jboolean finish) {
+    if (!resolve_fields(env)) return kGenericError;
+    const jsize in_n = inputEndExclusive > inputStart ? inputEndExclusive - inputStart : 0;
+    const jsize out_n = outputEndExclusive > outputStart ? outputEndExclusive - outputStart : 0;
+    std::vector<jbyte> in(static_cast<size_t>(in_n)), out(static_cast<size_t>(out_n));
+    if (in_n > 0) {
+        env->GetByteArrayRegion(inputByteArray, inputStart, in_n, in.data());
+        if (env->ExceptionCheck()) return kGenericError;
+    }
+    kzg_inBuffer ib = { in.data(), static_cast<size_t>(in_n), 0 };
+    kzg_outBuffer ob = { out.data(), static_cast<size_t>(out_n), 0 };
+    const size_t result = kzg_compressStream2(reinterpret_cast<kzg_CCtx*>(cctx), &ob, &ib, finish ? 2 : 0);
     if (ob.pos > 0) {
         env->SetByteArrayRegion(outputByteArray, outputStart, static_cast<jsize>(ob.pos), out.data());
         if (env->ExceptionCheck()) return kGenericError;

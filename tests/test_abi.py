@@ -86,7 +86,7 @@ def test_product_never_touches_oracle():
 
 def test_jni_shim_typechecks_and_names_the_reference_symbols():
     """Layer C (kzg_jni.cpp) cannot be linked without a JDK; check that it compiles against the minimal
-    jni.h stub and defines exactly the decompress-side symbols Kompressor's ZstdWrapper binds
+    jni.h stub and defines exactly the symbols Kompressor's ZstdWrapper binds (all ten externals of libzstd-jni.so)
     (kompressor-zstd--nativelib/src/jvmCommonMain/kotlin/com/ensody/kompressor/zstd/ZstdWrapper.kt:24-60)."""
     import subprocess
     src = os.path.join(ROOT, "kompressor_b200", "csrc", "kzg_jni.cpp")
@@ -96,4 +96,5 @@ def test_jni_shim_typechecks_and_names_the_reference_symbols():
     text = open(src).read()
     defined = set(re.findall(r"JNICALL\s+(Java_com_ensody_kompressor_zstd_ZstdWrapper_\w+|JNI_On\w+)\s*\(", text))
     assert defined == {"JNI_OnLoad", "JNI_OnUnload"} | {"Java_com_ensody_kompressor_zstd_ZstdWrapper_" + n for n in (
-        "createDecompressor", "freeDecompressor", "loadDecompressorDictionary", "decompressStream", "getErrorName")}
+        "createDecompressor", "freeDecompressor", "loadDecompressorDictionary", "decompressStream", "getErrorName",
+        "createCompressor", "freeCompressor", "setParameter", "loadCompressorDictionary", "compressStream")}
