@@ -32,10 +32,10 @@ struct kzg_enc {
     int sm_count = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr;
-    Buf tables, seq, chunks, tickets;            // workspace
+    Buf tables, seq, chunks, tickets, lit;       // workspace
     Buf st_src, st_dst, st_tab;                  // staging of the host-pointer API
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-    float stage_ms[3] = { 0, 0, 0 };
+    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    float stage_ms[4] = { 0, 0, 0, 0 };
     bool profiling = false;
 };
 
@@ -58,7 +58,7 @@ extern "C" int kzg_enc_create(kzg_enc** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
     e->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
-    for (int k = 0; k < 4; k++) cudaEventCreate(&e->ev[k]);
+    for (int k = 0; k < 5; k++) cudaEventCreate(&e->ev[k]);
     static KzgEncTables host_tables;
     kzg_enc_build_tables(host_tables);
     if (e->tables.ensure(sizeof(KzgEncTables)) || e->tickets.ensure(64) ||
@@ -75,8 +75,8 @@ extern "C" void kzg_enc_destroy(kzg_enc* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
-    for (int k = 0; k < 4; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
-    e->tables.release(); e->seq.release(); e->chunks.release(); e->tickets.release();
+    for (int k = 0; k < 5; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    e->tables.release(); e->seq.release(); e->chunks.release(); e->tickets.release(); e->lit.release();
     e->st_src.release(); e->st_dst.release(); e->st_tab.release();
     delete e;
 }
@@ -84,9 +84,9 @@ extern "C" void kzg_enc_destroy(kzg_enc* e) {
 extern "C" int kzg_enc_set_profiling(kzg_enc* e, int enable) { if (!e) return -(int)KZG_E_GENERIC; e->profiling = enable != 0; return 0; }
 
 extern "C" int kzg_enc_last_stage_ms(kzg_enc* e, float* ms, const char** names, int max_stages) {
-    static const char* const kNames[3] = { "match", "encode", "finish" };
+    static const char* const kNames[4] = { "match", "literals", "encode", "finish" };
     if (!e) return -(int)KZG_E_GENERIC;
-    int n = max_stages < 3 ? max_stages : 3;
+    int n = max_stages < 4 ? max_stages : 4;
     for (int k = 0; k < n; k++) { if (ms) ms[k] = e->stage_ms[k]; if (names) names[k] = kNames[k]; }
     return n;
 }
@@ -99,7 +99,9 @@ static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, con
     if (n > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
     if (max_chunk > KZG_BLOCK_MAX) max_chunk = KZG_BLOCK_MAX;       // larger chunks are reported per chunk (srcSize_wrong)
     const u32 seq_cap = KZG_ENC_WARPS * (u32)(max_chunk / (6 * KZG_ENC_WARPS) + 32);     // per part: one sequence per 6 bytes at most
-    if (e->seq.ensure((size_t)n * seq_cap * 8) || e->chunks.ensure((size_t)n * sizeof(KzgEncChunk))) return -(int)KZG_E_MEMORY;
+    const u32 lit_cap = (u32)((max_chunk + 15) & ~15ull) + 16;
+    if (e->seq.ensure((size_t)n * seq_cap * 8) || e->chunks.ensure((size_t)n * sizeof(KzgEncChunk)) || e->lit.ensure((size_t)n * lit_cap))
+        return -(int)KZG_E_MEMORY;
     KzgEncBatch B;
     memset(&B, 0, sizeof B);
     B.src = (const u8*)d_src; B.src_off = d_src_off; B.src_size = d_src_size;
@@ -107,6 +109,7 @@ static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, con
     B.status = d_status; B.out_size = d_out_size; B.n = (u32)n; B.flags = (u32)flags;
     B.seq = (u64*)e->seq.p; B.seq_cap = seq_cap; B.chunks = (KzgEncChunk*)e->chunks.p;
     B.tab = (const KzgEncTables*)e->tables.p; B.tickets = (u32*)e->tickets.p;
+    B.lit = (u8*)e->lit.p; B.lit_cap = lit_cap;
     CKE(cudaMemsetAsync(e->tickets.p, 0, 64, s));
     // the chunk area of the match kernel's shared memory: 64 KiB (two chunks per SM) unless the batch has larger chunks
     const u32 chunk_cap = max_chunk <= 65536 ? 65536u : KZG_BLOCK_MAX;
@@ -116,12 +119,14 @@ static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, con
     if (prof) cudaEventRecord(e->ev[0], s);
     kzg_enc_match_kernel<<<e->sm_count * per_sm, KZG_ENC_WARPS * 32, smem, s>>>(B, chunk_cap);
     if (prof) cudaEventRecord(e->ev[1], s);
-    kzg_enc_encode_kernel<<<e->sm_count * 4, KZG_ENC_EWARPS * 32, 0, s>>>(B);
+    kzg_enc_literals_kernel<<<e->sm_count * 8, KZG_ENC_HUF_THREADS, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[2], s);
-    kzg_enc_finish_kernel<<<e->sm_count * 8, 128, 0, s>>>(B);
+    kzg_enc_encode_kernel<<<e->sm_count * 4, KZG_ENC_EWARPS * 32, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[3], s);
+    kzg_enc_finish_kernel<<<e->sm_count * 8, 128, 0, s>>>(B);
+    if (prof) cudaEventRecord(e->ev[4], s);
     CKE(cudaGetLastError());
-    return 3;
+    return 4;
 }
 
 extern "C" int kzg_compress_batch_device(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, const uint64_t* d_src_size,
@@ -140,7 +145,7 @@ extern "C" int kzg_enc_finish(kzg_enc* e, void* stream) {
     CKE(cudaSetDevice(e->device));
     CKE(cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
     if (e->profiling)
-        for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&e->stage_ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) { cudaGetLastError(); e->stage_ms[k] = 0; }
+        for (int k = 0; k < 4; k++) if (cudaEventElapsedTime(&e->stage_ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) { cudaGetLastError(); e->stage_ms[k] = 0; }
     return 0;
 }
 
@@ -206,6 +211,6 @@ extern "C" int kzg_compress_batch_host(kzg_enc* e, const void* src, const uint64
     if (rc < 0) return rc;
     if (!ok) { cudaGetLastError(); return -(int)KZG_E_MEMORY; }
     if (e->profiling)
-        for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&e->stage_ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) { cudaGetLastError(); e->stage_ms[k] = 0; }
+        for (int k = 0; k < 4; k++) if (cudaEventElapsedTime(&e->stage_ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) { cudaGetLastError(); e->stage_ms[k] = 0; }
     return 0;
 }

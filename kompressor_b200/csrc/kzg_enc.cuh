@@ -5,13 +5,16 @@
 // encoder is interchangeable with it, because decoders only see the format (RFC 8878).
 // Parity bar for this side: libzstd 1.5.7 decodes every emitted frame to the original bytes.
 //
-// Format choices of this first version: one compressed block per frame with raw literals and the predefined
-// FSE tables (Appendix A.6), repeat-offset codes, optional XXH64 trailer; a raw block when that is not smaller.
+// Format choices of this version: one compressed block per frame, Huffman-coded literals (4 streams, direct weight
+// table, so symbols up to 128; raw literals otherwise), the predefined FSE tables (Appendix A.6), repeat-offset
+// codes, optional XXH64 trailer; a raw block when that is not smaller.
 //   match    CTA per chunk, the chunk staged in shared memory: each of the eight warps parses one eighth greedily with
 //            its own hash table of 4-byte strings (first filled with every earlier position of the chunk, so that
 //            candidates come from anywhere before): 32 positions probed per step, the first hit extended 128 bytes
 //            per step by the whole warp; then the warps gather the literal runs from shared memory to their final
 //            place in the frame
+//   literals CTA per chunk: histogram, length-limited Huffman code (11 bits), then the four streams in parallel, one
+//            warp each, 128 symbols per step at prefix-summed bit offsets; raw or RLE literals when that is smaller
 //   encode   warp per chunk: offsets -> repeat codes (forward, serial on one lane over coalesced loads), then the
 //            backward FSE bitstream 32 sequences at a time: three lanes run the three state chains, every lane
 //            assembles its sequence's bit fields at a prefix-summed bit offset in shared memory
@@ -36,7 +39,7 @@ struct KzgEncTables {
     u8 ll_code[64], ml_code[128];                     // code of small literal lengths / (match length - 3)
 };
 
-struct KzgEncChunk { u32 n_seq[KZG_ENC_WARPS]; u32 lit_size, state, total, pad; };   // n_seq: sequences of each part
+struct KzgEncChunk { u32 n_seq[KZG_ENC_WARPS]; u32 lit_size, state, total, lit_section; };   // n_seq: sequences of each part; lit_section: bytes of the literals section in the block
 
 struct KzgEncBatch {
     const u8* src; const u64* src_off; const u64* src_size;
@@ -45,8 +48,9 @@ struct KzgEncBatch {
     u32 n, flags;
     u64* seq; u32 seq_cap;                            // records per chunk, an eighth of them per part: ll[0,18) | ml[18,36) | off[36,54)
     KzgEncChunk* chunks;
+    u8* lit; u32 lit_cap;                             // literal bytes of chunk i, gathered by the match stage: lit + i * lit_cap
     const KzgEncTables* tab;
-    u32* tickets;                                     // [0] match, [1] finish, [2] encode
+    u32* tickets;                                     // [0] match, [1] finish, [2] encode, [3] literals
 };
 
 KZG_HD void kzg_wr16(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
@@ -160,6 +164,13 @@ KZG_HD u32 kzg_enc_offset_value(u32 ll, u32 off, u32& r0, u32& r1, u32& r2) {
     return ob;
 }
 
+// Header of a raw (type 0) or RLE (type 1) literals section with a 20-bit size: 3 bytes (Appendix A.3).
+KZG_HD void kzg_enc_write_lit_header(u8* blk, u32 type, u32 lit_size) {
+    blk[0] = (u8)(type | (3u << 2) | ((lit_size & 15u) << 4));
+    blk[1] = (u8)(lit_size >> 4);
+    blk[2] = (u8)(lit_size >> 12);
+}
+
 // Headers in front of the sequence bitstream. Returns where the bitstream starts, or NULL (raw block / error:
 // ck.state says which).
 KZG_HD u8* kzg_enc_block_prologue(const KzgEncBatch& B, u32 i, u32 nseq, u8*& blk, u8*& limit) {
@@ -170,14 +181,10 @@ KZG_HD u8* kzg_enc_block_prologue(const KzgEncBatch& B, u32 i, u32 nseq, u8*& bl
     if (n > KZG_BLOCK_MAX) { ck.state = KZG_ENC_ST_ERROR; B.status[i] = KZG_E_SRCSIZE_WRONG; B.out_size[i] = 0; return nullptr; }
     if (B.dst_cap[i] < kzg_enc_bound(n)) { ck.state = KZG_ENC_ST_ERROR; B.status[i] = KZG_E_DSTSIZE_TOO_SMALL; B.out_size[i] = 0; return nullptr; }
     const u32 hdr = kzg_enc_write_header(dst, n, (B.flags & KZG_ENC_FLAG_CHECKSUM) != 0);
-    const u32 lit_size = ck.lit_size;
     ck.state = KZG_ENC_ST_RAW;
-    if (nseq == 0) return nullptr;
+    if (nseq == 0 || ck.lit_section == 0) return nullptr;
     blk = dst + hdr + 3;
-    blk[0] = (u8)((3u << 2) | ((lit_size & 15u) << 4));          // raw literals, 20-bit size (3-byte header)
-    blk[1] = (u8)(lit_size >> 4);
-    blk[2] = (u8)(lit_size >> 12);
-    u8* p = blk + 3 + lit_size;
+    u8* p = blk + ck.lit_section;                                // the literals section is in place already
     limit = blk + n;                                             // a compressed block must be smaller than the raw one
     if (p + 4 >= limit) return nullptr;
     if (nseq < 128) *p++ = (u8)nseq;
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             if (threadIdx.x == 0) {
                 KzgEncChunk ck;
                 for (u32 q = 0; q < KZG_ENC_WARPS; q++) ck.n_seq[q] = 0;
-                ck.lit_size = 0; ck.state = 0; ck.total = 0; ck.pad = 0;
+                ck.lit_size = 0; ck.state = 0; ck.total = 0; ck.lit_section = 0;
                 B.chunks[i] = ck;
             }
             continue;
@@ -426,7 +433,7 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             lbase += misc[8 + q];
             carry = misc[q] ? misc[16 + q] : carry + misc[8 + q];
         }
-        u8* const lit = B.dst + B.dst_off[i] + kzg_enc_header_size(n) + 6 + lbase;
+        u8* const lit = B.lit + (size_t)i * B.lit_cap + lbase;
         u32 spos = q0, dpos = 0;
         for (u32 b = 0; b < nseq; b += 32) {
             const bool have = b + lane < nseq;
@@ -452,8 +459,205 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             KzgEncChunk ck;
             ck.lit_size = 0;
             for (u32 q = 0; q < KZG_ENC_WARPS; q++) { ck.n_seq[q] = misc[q]; ck.lit_size += misc[8 + q]; }
-            ck.state = 0; ck.total = 0; ck.pad = 0;
+            ck.state = 0; ck.total = 0; ck.lit_section = 0;
             B.chunks[i] = ck;
+        }
+    }
+}
+
+// literals stage: one CTA per chunk.  Reads the gathered literals from the workspace and writes the literals section
+// (Appendix A.3-A.4) to its place in the block: Huffman-coded in four streams, or raw / RLE.
+#define KZG_ENC_HUF_THREADS 128
+__global__ void __launch_bounds__(KZG_ENC_HUF_THREADS) kzg_enc_literals_kernel(KzgEncBatch B) {
+    using namespace kzg_encd;
+    __shared__ u32 hist[256];
+    __shared__ u32 wnode[512];                     // weights of the tree nodes (leaves in sorted order, then internal)
+    __shared__ u16 parent[512];
+    __shared__ u16 order[256];                     // present symbols by ascending count
+    __shared__ u8 len[256];                        // code length per symbol, 0 = absent
+    __shared__ u16 code[256];
+    __shared__ u32 stage[4][48];                   // per stream: 128 symbols x 11 bits + carry
+    __shared__ u32 misc[16];                       // [0] ticket, [1] max symbol, [2] mode, [3] maxbits, [4..8) stream bits, [8..12) stream offsets, [12] header bytes
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { misc[0] = atomicAdd(&B.tickets[3], 1u); misc[1] = 0; }
+        for (u32 k = tid; k < 256; k += blockDim.x) { hist[k] = 0; len[k] = 0; }
+        __syncthreads();
+        const u32 i = misc[0];
+        if (i >= B.n) break;
+        const KzgEncChunk ck = B.chunks[i];
+        u32 nseq = 0;
+#pragma unroll
+        for (int q = 0; q < KZG_ENC_WARPS; q++) nseq += ck.n_seq[q];
+        if (nseq == 0) continue;                                 // raw block anyway
+        const u32 n = (u32)B.src_size[i], nl = ck.lit_size;
+        const u8* lit = B.lit + (size_t)i * B.lit_cap;
+        u8* const blk = B.dst + B.dst_off[i] + kzg_enc_header_size(n) + 3;
+        // ---- histogram
+        {
+            const u32* lit4 = reinterpret_cast<const u32*>(lit);
+            const u32 nw = nl >> 2;
+            for (u32 k = tid; k < nw; k += blockDim.x) {
+                const u32 w = lit4[k];
+                atomicAdd(&hist[w & 255u], 1u); atomicAdd(&hist[(w >> 8) & 255u], 1u);
+                atomicAdd(&hist[(w >> 16) & 255u], 1u); atomicAdd(&hist[w >> 24], 1u);
+            }
+            for (u32 k = (nw << 2) + tid; k < nl; k += blockDim.x) atomicAdd(&hist[lit[k]], 1u);
+        }
+        __syncthreads();
+        u32 present = 0;
+        for (u32 k = tid; k < 256; k += blockDim.x) if (hist[k]) { present++; atomicMax(&misc[1], k); }
+        const u32 m = (u32)__syncthreads_count(present == 1) + 2u * (u32)__syncthreads_count(present == 2);
+        const u32 maxsym = misc[1];
+        // mode: 0 raw, 1 RLE, 2 Huffman
+        u32 mode = 2;
+        if (nl < 64 || maxsym > 128) mode = 0;
+        if (m == 1 && nl > 0) mode = 1;
+        if (mode == 2) {
+            // ---- present symbols by ascending count (rank sort), then the Huffman tree on one thread
+            for (u32 t = tid; t < 256; t += blockDim.x) {
+                const u32 c = hist[t];
+                if (c) {
+                    u32 r = 0;
+                    for (u32 j = 0; j < 256; j++) { const u32 cj = hist[j]; r += (cj != 0) && (cj < c || (cj == c && j < t)); }
+                    order[r] = (u16)t;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (u32 k = 0; k < m; k++) wnode[k] = hist[order[k]];
+                u32 maxd;
+                for (;;) {
+                    // two-queue merge: leaves [0, m) ascending, internal nodes [m, 2m-1) are created in ascending order
+                    u32 li = 0, ii = m, ni = m;
+                    for (u32 k = 0; k + 1 < m; k++) {
+                        u32 a, b;
+                        if (li < m && (ii >= ni || wnode[li] <= wnode[ii])) a = li++; else a = ii++;
+                        if (li < m && (ii >= ni || wnode[li] <= wnode[ii])) b = li++; else b = ii++;
+                        wnode[ni] = wnode[a] + wnode[b];
+                        parent[a] = parent[b] = (u16)ni;
+                        ni++;
+                    }
+                    // depths from the root down (a parent always has a larger index than its children); the weights of
+                    // internal nodes are not needed any more, so their slots hold the depths
+                    const u32 root = 2 * m - 2;
+                    maxd = 0;
+                    wnode[root] = 0;
+                    for (u32 v = root; v-- > 0;) {
+                        const u32 d = wnode[parent[v]] + 1u;
+                        if (v >= m) wnode[v] = d;
+                        else { len[order[v]] = (u8)d; if (d > maxd) maxd = d; }
+                    }
+                    if (maxd <= KZG_HUF_MAXBITS) break;
+                    // too deep: flatten the counts and build again (the order stays valid)
+                    for (u32 k = 0; k < m; k++) { const u32 c = hist[order[k]]; const u32 h2 = (c + 1) >> 1; hist[order[k]] = h2 ? h2 : 1; wnode[k] = hist[order[k]]; }
+                }
+                misc[3] = maxd;
+            }
+            __syncthreads();
+            const u32 maxbits = misc[3];
+            // ---- canonical codes, the way the decoder fills its table: by weight (longest codes first), then by symbol
+            for (u32 t = tid; t < 256; t += blockDim.x) {
+                const u32 l = len[t];
+                if (l) {
+                    const u32 w = maxbits + 1 - l;
+                    u32 below = 0, r = 0;                                // table entries of lower weights; same-weight symbols before t
+                    for (u32 j = 0; j < 256; j++) {
+                        const u32 lj = len[j];
+                        if (lj > l) below += 1u << (maxbits - lj);       // weight wj < w: 2^(wj-1) = 2^(maxbits-lj) entries
+                        r += (lj == l) && (j < t);
+                    }
+                    code[t] = (u16)((below >> (w - 1)) + r);
+                }
+            }
+            __syncthreads();
+            // ---- bits of each stream
+            const u32 seg = (nl + 3) >> 2;
+            {
+                const u32 s0 = min(warp * seg, nl), s1 = min(s0 + seg, nl);
+                u32 bitsum = 0;
+                for (u32 k = s0 + lane; k < s1; k += 32) bitsum += len[lit[k]];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) bitsum += __shfl_xor_sync(0xFFFFFFFFu, bitsum, o);
+                if (lane == 0) misc[4 + warp] = bitsum;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const u32 whdr = 1 + ((maxsym + 1) >> 1);               // header byte + maxsym weights, two per byte
+                const u32 sz0 = (misc[4] + 8) >> 3, sz1 = (misc[5] + 8) >> 3, sz2 = (misc[6] + 8) >> 3, sz3 = (misc[7] + 8) >> 3;
+                const u32 csize = whdr + 6 + sz0 + sz1 + sz2 + sz3;
+                const u32 big = nl > csize ? nl : csize;
+                const u32 fmt = big < 1024 ? 1u : (big < 16384 ? 2u : 3u), lhdr = 2 + fmt, fbits = fmt == 1 ? 10u : (fmt == 2 ? 14u : 18u);
+                if (lhdr + csize >= 3 + nl || sz0 > 65535 || sz1 > 65535 || sz2 > 65535) misc[2] = 0;      // raw is not larger
+                else {
+                    misc[2] = 2;
+                    const u64 h = 2ull | ((u64)fmt << 2) | ((u64)nl << 4) | ((u64)csize << (4 + fbits));
+                    for (u32 k = 0; k < lhdr; k++) blk[k] = (u8)(h >> (8 * k));
+                    u8* p = blk + lhdr;
+                    *p++ = (u8)(127 + maxsym);
+                    for (u32 k = 0; k < maxsym; k += 2) {
+                        const u32 w0 = len[k] ? maxbits + 1 - len[k] : 0u, w1 = (k + 1 < maxsym && len[k + 1]) ? maxbits + 1 - len[k + 1] : 0u;
+                        *p++ = (u8)((w0 << 4) | w1);
+                    }
+                    kzg_wr16(p, sz0); kzg_wr16(p + 2, sz1); kzg_wr16(p + 4, sz2);
+                    const u32 base = lhdr + whdr + 6;
+                    misc[8] = base; misc[9] = base + sz0; misc[10] = base + sz0 + sz1; misc[11] = base + sz0 + sz1 + sz2;
+                    misc[12] = lhdr + csize;
+                }
+            }
+            __syncthreads();
+            mode = misc[2];
+            if (mode == 2) {
+                // ---- the four streams, one warp each: symbols from the last to the first, 128 per step
+                const u32 s0 = min(warp * seg, nl), s1 = min(s0 + seg, nl);
+                u8* out = blk + misc[8 + warp];
+                u32* st = stage[warp];
+                u32 carry_bits = 0, carry_n = 0;
+                for (u32 hi = s1; hi > s0;) {
+                    const u32 cnt = min(128u, hi - s0);
+                    // this lane's (at most four) symbols, in the order they are written: hi-1-4*lane, hi-2-4*lane, ...
+                    u64 v = 0;
+                    u32 vn = 0;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const u32 j = 4 * lane + t;
+                        if (j < cnt) {
+                            const u32 sym = lit[hi - 1 - j];
+                            v |= (u64)code[sym] << vn;
+                            vn += len[sym];
+                        }
+                    }
+                    const u32 incl = warp_incl_sum(vn, lane);
+                    const u32 total = carry_n + __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    for (u32 k = lane; k < 48; k += 32) st[k] = k == 0 ? carry_bits : 0u;
+                    __syncwarp();
+                    if (vn) {
+                        const u32 bp = carry_n + incl - vn;
+                        const u32 sh = bp & 31u;
+                        atomicOr(&st[bp >> 5], (u32)(v << sh));
+                        const u64 hi64 = sh ? (v >> (32 - sh)) : (v >> 32);       // bits that did not fit the first word
+                        if ((u32)hi64) atomicOr(&st[(bp >> 5) + 1], (u32)hi64);
+                        if ((u32)(hi64 >> 32)) atomicOr(&st[(bp >> 5) + 2], (u32)(hi64 >> 32));
+                    }
+                    __syncwarp();
+                    const u32 nbytes = total >> 3;
+                    for (u32 k = lane; k < nbytes; k += 32) out[k] = (u8)(st[k >> 2] >> (8 * (k & 3)));
+                    carry_n = total & 7u;
+                    carry_bits = carry_n ? (st[nbytes >> 2] >> (8 * (nbytes & 3))) & 0xFFu : 0u;
+                    out += nbytes;
+                    hi -= cnt;
+                    __syncwarp();
+                }
+                if (lane == 0) *out = (u8)(carry_bits | (1u << carry_n));       // end mark above the last bits
+                if (tid == 0) B.chunks[i].lit_section = misc[12];
+            }
+        }
+        if (mode == 1) {
+            if (tid == 0) { kzg_enc_write_lit_header(blk, 1, nl); blk[3] = lit[0]; B.chunks[i].lit_section = 4; }
+        } else if (mode == 0) {
+            if (tid == 0) { kzg_enc_write_lit_header(blk, 0, nl); B.chunks[i].lit_section = 3 + nl; }
+            for (u32 k = tid; k < nl; k += blockDim.x) blk[3 + k] = lit[k];
         }
     }
 }

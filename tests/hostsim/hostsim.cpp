@@ -153,7 +153,7 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
     for (u32 i = 0; i < n; i++) {
         KzgEncChunk& ck = chunks[i];
         for (u32 q = 0; q < KZG_ENC_WARPS; q++) ck.n_seq[q] = 0;
-        ck.lit_size = 0; ck.state = 0; ck.total = 0; ck.pad = 0;
+        ck.lit_size = 0; ck.state = 0; ck.total = 0; ck.lit_section = 0;
         const u32 len = (u32)src_size[i];
         if (src_size[i] > KZG_BLOCK_MAX || dst_cap[i] < kzg_enc_bound(len) || len < 64) continue;
         const u8* s = src + src_off[i];
@@ -177,6 +177,8 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
         }
         memcpy(lit + ck.lit_size, s + anchor, len - anchor);
         ck.lit_size += len - anchor;
+        kzg_enc_write_lit_header(lit - 3, 0, ck.lit_size);               // raw literals section, in place
+        ck.lit_section = 3 + ck.lit_size;
     }
     for (u32 i = 0; i < n; i++) kzg_enc_stage_encode(B, i);
     for (u32 i = 0; i < n; i++) {
