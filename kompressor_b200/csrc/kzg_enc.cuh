@@ -281,6 +281,15 @@ __device__ __forceinline__ u32 lds32u(u32 a) {
     const u32 b = a & ~3u;
     return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) << 3);
 }
+// the 4 bytes at shared address a and the table slot of the 5 bytes there (longer context: candidates that are more
+// likely to be long matches)
+__device__ __forceinline__ u32 lds32u_hash5(u32 a, u32& h) {
+    const u32 b = a & ~3u, sh = (a & 3u) << 3;
+    const u32 w0 = lds32(b), w1 = lds32(b + 4), w2 = lds32(b + 8);
+    const u32 v = __funnelshift_r(w0, w1, sh);
+    h = ((v * 2654435761u) ^ ((__funnelshift_r(w1, w2, sh) & 0xFFFFu) * 0x9E3779B1u)) * 0x85EBCA6Bu >> (32 - KZG_ENC_HASH_LOG);
+    return v;
+}
 // unaligned 32-bit read from global memory (two aligned words; reads up to 7 bytes past p)
 __device__ __forceinline__ u32 rd32u(const u8* p) {
     const u32* q = reinterpret_cast<const u32*>((uintptr_t)p & ~(uintptr_t)3);
@@ -365,6 +374,9 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
         }
         __syncthreads();
         const u32 base = s_chunk + shift;                       // shared address of chunk byte 0
+        // what hashing may read beyond the chunk is fixed, so that the output depends on the chunk alone
+        if (threadIdx.x < 16) sm[shift + n + threadIdx.x] = 0;
+        __syncthreads();
         // ---- this warp's part
         const u32 qlen = (((n + KZG_ENC_WARPS - 1) / KZG_ENC_WARPS) + 31u) & ~31u;
         const u32 q0 = min(warp * qlen, n), q1 = min(q0 + qlen, n);
@@ -375,21 +387,25 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
         __syncwarp();
         for (u32 p0 = 0; p0 < q0; p0 += 32) {                   // q0 is a multiple of 32
             const u32 p = p0 + lane;
-            const u32 v = lds32u(base + p);
-            table[(v * 2654435761u) >> (32 - KZG_ENC_HASH_LOG)] = (u16)p;
+            u32 h;
+            lds32u_hash5(base + p, h);
+            table[h] = (u16)p;
         }
         __syncwarp();
-        u32 pos = q0, anchor = q0, nseq = 0, nlit = 0;
+        u32 pos = q0, anchor = q0, nseq = 0, nlit = 0, rep = 0xFFFFFFFFu;
         const u32 limit = q1 >= 3 ? q1 - 3 : 0;                  // probed positions have their 4 bytes inside the part
         while (pos < limit) {
             const u32 p = pos + lane;
             const bool ok = p < limit;
-            const u32 v = lds32u(base + p);
-            const u32 h = (v * 2654435761u) >> (32 - KZG_ENC_HASH_LOG);
+            u32 h;
+            const u32 v = lds32u_hash5(base + p, h);
             // the table keeps the low 16 bits of positions: the candidate is the nearest earlier position with them
             i32 cand = (i32)((p & ~0xFFFFu) | (u32)table[h]);
             if (cand >= (i32)p) cand -= 65536;
-            const bool hit = ok && cand >= 0 && lds32u(base + (u32)cand) == v;
+            // the distance of the previous match first: it costs a repeat code instead of a full offset
+            const bool rep_hit = ok && p >= rep && lds32u(base + p - rep) == v;
+            if (rep_hit) cand = (i32)(p - rep);
+            const bool hit = rep_hit || (ok && cand >= 0 && lds32u(base + (u32)cand) == v);
             const u32 m = __ballot_sync(0xFFFFFFFFu, hit);
             // positions up to the match start enter the table; the ones behind it are probed again by a later step
             // and must still find their older candidates then
@@ -397,9 +413,15 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             if (ok && lane <= l) table[h] = (u16)p;
             __syncwarp();
             if (m == 0) { pos += 32; continue; }
-            const u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
-            // forward extension inside the part, 128 bytes per step
+            u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
             u32 len = 4;
+            {   // backward extension into the pending literals (at most 32 bytes)
+                const bool same = ms > anchor + lane && mc > lane && lds8(base + ms - 1 - lane) == lds8(base + mc - 1 - lane);
+                const u32 stop = __ballot_sync(0xFFFFFFFFu, !same);
+                const u32 back = stop ? __ffs(stop) - 1 : 32u;
+                ms -= back; mc -= back; len += back;
+            }
+            // forward extension inside the part, 128 bytes per step
             for (;;) {
                 const u32 k = len + 4 * lane;
                 const i32 rem = (i32)q1 - (i32)(ms + k);             // bytes of this lane's word that belong to the part
@@ -422,6 +444,7 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             nseq++;
             nlit += ll;
             anchor = pos = ms + len;
+            rep = ms - mc;
             if (nseq == qcap) break;
         }
         const u32 tail = q1 - anchor;
