@@ -6,8 +6,9 @@
 // Parity bar for this side: libzstd 1.5.7 decodes every emitted frame to the original bytes.
 //
 // Format choices of this version: one compressed block per frame, Huffman-coded literals (4 streams, direct weight
-// table, so symbols up to 128; raw literals otherwise), the predefined FSE tables (Appendix A.6), repeat-offset
-// codes, optional XXH64 trailer; a raw block when that is not smaller.
+// table, so symbols up to 128; raw literals otherwise), sequence tables made for the block (FSE mode; RLE mode for a
+// single code; the predefined tables for short blocks, Appendix A.6), repeat-offset codes, optional XXH64 trailer;
+// a raw block when that is not smaller.
 //   match    CTA per chunk, the chunk staged in shared memory: each of the eight warps parses one eighth greedily with
 //            its own hash table of 4-byte strings (first filled with every earlier position of the chunk, so that
 //            candidates come from anywhere before): 32 positions probed per step, the first hit extended 128 bytes
@@ -73,10 +74,9 @@ KZG_HD u64 kzg_enc_bound(u64 n) { return n + 32; }
 
 // ---------------------------------------------------------------------------------------------
 // FSE encoding tables of a normalised distribution (the mirror image of the decode-table build, Appendix A.5).
-inline void kzg_enc_build_ctable(const i16* norm, u32 nsym, u32 log, u16* state_table, u32* dnb, i32* dfs) {
+// scratch: 66 words + (1 << log) bytes.
+KZG_HD void kzg_enc_build_ctable(const i16* norm, u32 nsym, u32 log, u16* state_table, u32* dnb, i32* dfs, u32* cumul, u8* symbol_of) {
     const u32 size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
-    u32 cumul[66];
-    u8 symbol_of[512];
     u32 high = size - 1;
     cumul[0] = 0;
     for (u32 s = 0; s < nsym; s++) {
@@ -110,9 +110,11 @@ inline void kzg_enc_build_tables(KzgEncTables& t) {
     KzgFseDesc d;
     kzg_default_fse_desc(d);
     memset(&t, 0, sizeof t);
-    kzg_enc_build_ctable(d.norm[0], 36, 6, t.st_ll, t.dnb_ll, t.dfs_ll);
-    kzg_enc_build_ctable(d.norm[1], 29, 5, t.st_of, t.dnb_of, t.dfs_of);
-    kzg_enc_build_ctable(d.norm[2], 53, 6, t.st_ml, t.dnb_ml, t.dfs_ml);
+    u32 cumul[66];
+    u8 symbol_of[64];
+    kzg_enc_build_ctable(d.norm[0], 36, 6, t.st_ll, t.dnb_ll, t.dfs_ll, cumul, symbol_of);
+    kzg_enc_build_ctable(d.norm[1], 29, 5, t.st_of, t.dnb_of, t.dfs_of, cumul, symbol_of);
+    kzg_enc_build_ctable(d.norm[2], 53, 6, t.st_ml, t.dnb_ml, t.dfs_ml, cumul, symbol_of);
     kzg_code_tables(t.ll_tab, t.ml_tab);
     for (u32 v = 0; v < 64; v++)
         for (u32 c = 0; c < 36; c++) { const u32 b = t.ll_tab[c] & 0xFFFFFFu, x = t.ll_tab[c] >> 24; if (v >= b && v < b + (1u << x)) t.ll_code[v] = (u8)c; }
@@ -148,6 +150,126 @@ KZG_HD void kzg_fsec_encode(KzgBitW& w, KzgFseC& s, const u16* st, const u32* dn
 
 KZG_HD u32 kzg_enc_ll_code(const KzgEncTables* t, u32 ll) { return ll < 64 ? (u32)t->ll_code[ll] : (u32)kzg_highbit(ll) + 19u; }
 KZG_HD u32 kzg_enc_ml_code(const KzgEncTables* t, u32 mlbase) { return mlbase < 128 ? (u32)t->ml_code[mlbase] : (u32)kzg_highbit(mlbase) + 36u; }
+
+// The three encoding tables one block is written with.  Index: 0 LL, 1 ML, 2 OF.
+struct KzgEncTabSet {
+    u16 st[1280];                   // state tables: LL at 0 (<= 512), ML at 512 (<= 512), OF at 1024 (<= 256)
+    u32 dnb[128];                   // deltaNbBits: LL at 0, ML at 36, OF at 89
+    i32 dfs[128];                   // deltaFindState, same layout
+    u32 log[3];                     // accuracy log; 0 = RLE mode (the state carries no bits)
+};
+#define KZG_ENC_ST_OFF(t) ((t) == 0 ? 0u : ((t) == 1 ? 512u : 1024u))
+#define KZG_ENC_SYM_OFF(t) ((t) == 0 ? 0u : ((t) == 1 ? 36u : 89u))
+struct KzgEncTabScratch { u32 cumul[66]; i16 norm[64]; u8 symbol_of[512]; };
+
+// the same on a table set: t = 0 LL, 1 ML, 2 OF
+KZG_HD void kzg_fsec_init_set(KzgFseC& s, const KzgEncTabSet& ts, u32 t, u32 sym) {
+    if (ts.log[t] == 0) { s.value = 1; return; }             // RLE mode
+    kzg_fsec_init(s, ts.st + KZG_ENC_ST_OFF(t), ts.dnb + KZG_ENC_SYM_OFF(t), ts.dfs + KZG_ENC_SYM_OFF(t), sym);
+}
+KZG_HD void kzg_fsec_encode_set(KzgBitW& w, KzgFseC& s, const KzgEncTabSet& ts, u32 t, u32 sym) {
+    kzg_fsec_encode(w, s, ts.st + KZG_ENC_ST_OFF(t), ts.dnb + KZG_ENC_SYM_OFF(t), ts.dfs + KZG_ENC_SYM_OFF(t), sym);
+}
+
+// Counts -> normalised counts that sum to 1 << log; every present symbol keeps at least 1 (Appendix A.5).
+KZG_HD void kzg_enc_normalize(const u32* cnt, u32 nsym, u32 total, u32 log, i16* norm) {
+    const u32 target = 1u << log;
+    u32 sum = 0, imax = 0, pmax = 0;
+    for (u32 s = 0; s < nsym; s++) {
+        u32 pr = 0;
+        if (cnt[s]) { pr = (u32)((((u64)cnt[s] << log) + (total >> 1)) / total); if (pr == 0) pr = 1; }
+        norm[s] = (i16)pr;
+        sum += pr;
+        if (pr > pmax) { pmax = pr; imax = s; }
+    }
+    if (sum < target) norm[imax] = (i16)(norm[imax] + (target - sum));
+    while (sum > target) {                                  // take the excess from the largest entries
+        u32 im = 0, pm = 0;
+        for (u32 s = 0; s < nsym; s++) if ((u32)norm[s] > pm) { pm = (u32)norm[s]; im = s; }
+        const u32 d = pm - 1 < sum - target ? pm - 1 : sum - target;
+        norm[im] = (i16)(pm - d);
+        sum -= d;
+    }
+}
+
+// FSE table description (Appendix A.5), the inverse of kzg_read_ncount.  Returns bytes written, 0 if they do not fit.
+KZG_HD u32 kzg_enc_write_ncount(u8* dst, u32 cap, const i16* norm, u32 nsym, u32 log) {
+    KzgBitW w;
+    w.acc = 0; w.nbits = 0; w.p = dst; w.end = dst + cap; w.ovf = false;
+    kzg_bw_add(w, log - 5, 4);
+    i32 remaining = 1 << log;
+    u32 s = 0;
+    while (remaining > 0 && s < nsym) {
+        const u32 bits = (u32)kzg_highbit((u32)remaining + 1) + 1;
+        const u32 lower = (1u << (bits - 1)) - 1, thr = (1u << bits) - 1 - ((u32)remaining + 1);
+        const u32 val = (u32)(norm[s] + 1);
+        if (val < thr) kzg_bw_add(w, val, bits - 1);
+        else if (val <= lower) kzg_bw_add(w, val, bits);
+        else kzg_bw_add(w, val + thr, bits);
+        remaining -= norm[s];
+        const bool zero = norm[s] == 0;
+        s++;
+        if (zero) {                                          // how many more zero-probability symbols follow
+            u32 n0 = 0;
+            while (s + n0 < nsym && norm[s + n0] == 0) n0++;
+            s += n0;
+            while (n0 >= 3) { kzg_bw_add(w, 3, 2); n0 -= 3; kzg_bw_flush(w); }
+            kzg_bw_add(w, n0, 2);
+        }
+        kzg_bw_flush(w);
+    }
+    if (w.nbits) { if (w.p < w.end) *w.p = (u8)w.acc; else w.ovf = true; w.p++; }
+    return (w.ovf || remaining != 0) ? 0u : (u32)(w.p - dst);
+}
+
+// Chooses the mode of each sequence table from the code histograms (hist: LL at 0, ML at 36, OF at 89), writes the
+// modes byte (at p[-1]) and the table descriptions at p, fills `ts`.  Returns the new write position (NULL: no room).
+KZG_HD u8* kzg_enc_prepare_tables(const KzgEncTables* T, u32 nseq, const u32* hist, KzgEncTabSet& ts, KzgEncTabScratch& sc, u8* p, u8* limit) {
+    u8* const modes_byte = p - 1;
+    const u32 nsym_of[3] = { 36, 53, 32 }, max_log[3] = { 9, 9, 8 }, pre_log[3] = { 6, 6, 5 };
+    u32 mode[3];
+    // descriptions are stored in the order LL, OF, ML (Appendix A.6)
+    const u32 order[3] = { 0, 2, 1 };
+    for (u32 k = 0; k < 3; k++) {
+        const u32 t = order[k];
+        const u32* h = hist + KZG_ENC_SYM_OFF(t);
+        u16* st = ts.st + KZG_ENC_ST_OFF(t);
+        u32* dnb = ts.dnb + KZG_ENC_SYM_OFF(t);
+        i32* dfs = ts.dfs + KZG_ENC_SYM_OFF(t);
+        u32 present = 0, last = 0;
+        for (u32 s = 0; s < nsym_of[t]; s++) if (h[s]) { present++; last = s; }
+        if (present == 1 && nseq >= 8) {                     // RLE mode: one byte, no state bits
+            mode[t] = 1;
+            if (p >= limit) return nullptr;
+            *p++ = (u8)last;
+            ts.log[t] = 0;
+            st[0] = 1; dnb[last] = 0; dfs[last] = -1;
+        } else if (nseq >= 128 && present > 1) {             // FSE mode: a table made for this block
+            mode[t] = 2;
+            u32 log = (u32)kzg_highbit(nseq - 1) - 2;
+            const u32 min_log = (u32)kzg_highbit(last) + 2;
+            if (log < min_log) log = min_log;
+            if (log < 5) log = 5;
+            if (log > max_log[t]) log = max_log[t];
+            kzg_enc_normalize(h, last + 1, nseq, log, sc.norm);
+            const u32 nb = kzg_enc_write_ncount(p, (u32)(limit - p), sc.norm, last + 1, log);
+            if (nb == 0) return nullptr;
+            p += nb;
+            ts.log[t] = log;
+            kzg_enc_build_ctable(sc.norm, last + 1, log, st, dnb, dfs, sc.cumul, sc.symbol_of);
+        } else {                                             // predefined
+            mode[t] = 0;
+            ts.log[t] = pre_log[t];
+            const u16* pst = t == 0 ? T->st_ll : (t == 1 ? T->st_ml : T->st_of);
+            const u32* pdnb = t == 0 ? T->dnb_ll : (t == 1 ? T->dnb_ml : T->dnb_of);
+            const i32* pdfs = t == 0 ? T->dfs_ll : (t == 1 ? T->dfs_ml : T->dfs_of);
+            for (u32 u = 0; u < (1u << pre_log[t]); u++) st[u] = pst[u];
+            for (u32 s = 0; s < nsym_of[t]; s++) { dnb[s] = pdnb[s]; dfs[s] = pdfs[s]; }
+        }
+    }
+    *modes_byte = (u8)((mode[0] << 6) | (mode[2] << 4) | (mode[1] << 2));     // LL, OF, ML
+    return p;
+}
 
 // Repeat-offset code of a distance (Appendix A.7); updates the history like the decoder will.
 KZG_HD u32 kzg_enc_offset_value(u32 ll, u32 off, u32& r0, u32& r1, u32& r2) {
@@ -190,7 +312,7 @@ KZG_HD u8* kzg_enc_block_prologue(const KzgEncBatch& B, u32 i, u32 nseq, u8*& bl
     if (nseq < 128) *p++ = (u8)nseq;
     else if (nseq < 0x7F00) { *p++ = (u8)((nseq >> 8) + 0x80); *p++ = (u8)nseq; }
     else { *p++ = 0xFF; kzg_wr16(p, nseq - 0x7F00); p += 2; }
-    *p++ = 0;                                                    // predefined LL / OF / ML tables
+    *p++ = 0;                                                    // modes byte (kzg_enc_prepare_tables fills it in)
     return p;
 }
 KZG_HD void kzg_enc_block_epilogue(const KzgEncBatch& B, u32 i, u8* blk, u8* end) {
@@ -220,15 +342,23 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
     if (!p) return;
     const KzgEncTables* T = B.tab;
     u64* seq = B.seq + (size_t)i * B.seq_cap;
-    {   // forward: distances -> offset values with repeat codes, in place
+    u32 hist[128];
+    for (u32 k = 0; k < 128; k++) hist[k] = 0;
+    {   // forward: distances -> offset values with repeat codes, in place; code histograms
         u32 r0 = 1, r1 = 4, r2 = 8;
         for (u32 s = 0; s < nseq; s++) {
             u64* r = kzg_enc_seq_at(seq, qcap, nq, s);
             const u64 rec = *r;
-            const u32 ob = kzg_enc_offset_value((u32)rec & 0x3FFFFu, (u32)(rec >> 36) & 0x3FFFFu, r0, r1, r2);
+            const u32 ll = (u32)rec & 0x3FFFFu, mlb = ((u32)(rec >> 18) & 0x3FFFFu) - 3u;
+            const u32 ob = kzg_enc_offset_value(ll, (u32)(rec >> 36) & 0x3FFFFu, r0, r1, r2);
             *r = (rec & 0xFFFFFFFFFull) | ((u64)ob << 36);
+            hist[kzg_enc_ll_code(T, ll)]++; hist[36 + kzg_enc_ml_code(T, mlb)]++; hist[89 + (u32)kzg_highbit(ob)]++;
         }
     }
+    KzgEncTabSet ts;
+    KzgEncTabScratch sc;
+    p = kzg_enc_prepare_tables(T, nseq, hist, ts, sc, p, limit);
+    if (!p) return;
     // backward: the last sequence initialises the states, the first is written last
     KzgBitW w;
     w.acc = 0; w.nbits = 0; w.p = p; w.end = limit; w.ovf = false;
@@ -237,9 +367,9 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
         const u64 rec = *kzg_enc_seq_at(seq, qcap, nq, nseq - 1);
         const u32 ll = (u32)rec & 0x3FFFFu, mlb = ((u32)(rec >> 18) & 0x3FFFFu) - 3u, ob = (u32)(rec >> 36) & 0x3FFFFu;
         const u32 cl = kzg_enc_ll_code(T, ll), cm = kzg_enc_ml_code(T, mlb), co = (u32)kzg_highbit(ob);
-        kzg_fsec_init(sML, T->st_ml, T->dnb_ml, T->dfs_ml, cm);
-        kzg_fsec_init(sOF, T->st_of, T->dnb_of, T->dfs_of, co);
-        kzg_fsec_init(sLL, T->st_ll, T->dnb_ll, T->dfs_ll, cl);
+        kzg_fsec_init_set(sML, ts, 1, cm);
+        kzg_fsec_init_set(sOF, ts, 2, co);
+        kzg_fsec_init_set(sLL, ts, 0, cl);
         kzg_bw_add(w, ll, T->ll_tab[cl] >> 24);
         kzg_bw_add(w, mlb, T->ml_tab[cm] >> 24);
         kzg_bw_flush(w);
@@ -250,9 +380,9 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
         const u64 rec = *kzg_enc_seq_at(seq, qcap, nq, s);
         const u32 ll = (u32)rec & 0x3FFFFu, mlb = ((u32)(rec >> 18) & 0x3FFFFu) - 3u, ob = (u32)(rec >> 36) & 0x3FFFFu;
         const u32 cl = kzg_enc_ll_code(T, ll), cm = kzg_enc_ml_code(T, mlb), co = (u32)kzg_highbit(ob);
-        kzg_fsec_encode(w, sOF, T->st_of, T->dnb_of, T->dfs_of, co);
-        kzg_fsec_encode(w, sML, T->st_ml, T->dnb_ml, T->dfs_ml, cm);
-        kzg_fsec_encode(w, sLL, T->st_ll, T->dnb_ll, T->dfs_ll, cl);
+        kzg_fsec_encode_set(w, sOF, ts, 2, co);
+        kzg_fsec_encode_set(w, sML, ts, 1, cm);
+        kzg_fsec_encode_set(w, sLL, ts, 0, cl);
         kzg_bw_add(w, ll, T->ll_tab[cl] >> 24);
         kzg_bw_flush(w);
         kzg_bw_add(w, mlb, T->ml_tab[cm] >> 24);
@@ -260,9 +390,9 @@ KZG_HD void kzg_enc_stage_encode(const KzgEncBatch& B, u32 i) {
         kzg_bw_flush(w);
         if (w.ovf) return;                                       // not smaller than raw
     }
-    kzg_bw_add(w, sML.value, 6);
-    kzg_bw_add(w, sOF.value, 5);
-    kzg_bw_add(w, sLL.value, 6);
+    kzg_bw_add(w, sML.value, ts.log[1]);
+    kzg_bw_add(w, sOF.value, ts.log[2]);
+    kzg_bw_add(w, sLL.value, ts.log[0]);
     kzg_bw_add(w, 1, 1);                                         // end mark
     kzg_bw_flush(w);
     if (w.nbits) { if (w.p < w.end) *w.p = (u8)w.acc; else w.ovf = true; w.p++; }
@@ -694,15 +824,15 @@ __global__ void __launch_bounds__(KZG_ENC_EWARPS * 32) kzg_enc_encode_kernel(Kzg
     __shared__ u32 s_chain[KZG_ENC_EWARPS][3][32];
     __shared__ u32 s_bits[KZG_ENC_EWARPS][KZG_ENC_STAGE_WORDS];
     __shared__ KzgEncTables s_tab;
-    __shared__ uint2 s_delta[36 + 53 + 32];        // {deltaNbBits, deltaFindState} of LL | ML | OF symbols
-    __shared__ u32 s_syms[KZG_ENC_EWARPS][100];    // per warp: codes of the batch (3 x 32), final states (3)
+    __shared__ KzgEncTabSet s_set[KZG_ENC_EWARPS];         // the tables the warp's current block is written with
+    __shared__ KzgEncTabScratch s_scr[KZG_ENC_EWARPS];
+    __shared__ u32 s_hist[KZG_ENC_EWARPS][128];            // code histograms: LL at 0, ML at 36, OF at 89
+    __shared__ u32 s_syms[KZG_ENC_EWARPS][100];            // per warp: codes of the batch (3 x 32), final states (3)
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 k = threadIdx.x; k < sizeof(KzgEncTables) / 4; k += blockDim.x) reinterpret_cast<u32*>(&s_tab)[k] = reinterpret_cast<const u32*>(B.tab)[k];
     __syncthreads();
-    for (u32 k = threadIdx.x; k < 36 + 53 + 32; k += blockDim.x)
-        s_delta[k] = k < 36 ? make_uint2(s_tab.dnb_ll[k], (u32)s_tab.dfs_ll[k])
-                            : (k < 89 ? make_uint2(s_tab.dnb_ml[k - 36], (u32)s_tab.dfs_ml[k - 36]) : make_uint2(s_tab.dnb_of[k - 89], (u32)s_tab.dfs_of[k - 89]));
-    __syncthreads();
+    KzgEncTabSet& ts = s_set[warp];
+    u32* hist = s_hist[warp];
     u32* syms = s_syms[warp];
     const KzgEncTables* T = &s_tab;
     u32* chain = &s_chain[warp][0][0];
@@ -726,6 +856,8 @@ __global__ void __launch_bounds__(KZG_ENC_EWARPS * 32) kzg_enc_encode_kernel(Kzg
         u64* seq = B.seq + (size_t)i * B.seq_cap;
         // ---- forward: offset values with repeat codes.  Loads and stores are coalesced, the history walk runs on
         // every lane redundantly (uniform control flow, no divergence) over shuffled records.
+        for (u32 k = lane; k < 128; k += 32) hist[k] = 0;
+        __syncwarp();
         {
             u32 r0 = 1, r1 = 4, r2 = 8;
 #pragma unroll 1
@@ -742,10 +874,20 @@ __global__ void __launch_bounds__(KZG_ENC_EWARPS * 32) kzg_enc_encode_kernel(Kzg
                         const u32 ob = kzg_enc_offset_value((u32)rj & 0x3FFFFu, (u32)(rj >> 36) & 0x3FFFFu, r0, r1, r2);
                         if (j == lane) mine = ob;
                     }
-                    if (have) sq[b + lane] = (rec & 0xFFFFFFFFFull) | ((u64)mine << 36);
+                    if (have) {
+                        sq[b + lane] = (rec & 0xFFFFFFFFFull) | ((u64)mine << 36);
+                        atomicAdd(&hist[kzg_enc_ll_code(T, (u32)rec & 0x3FFFFu)], 1u);
+                        atomicAdd(&hist[36 + kzg_enc_ml_code(T, ((u32)(rec >> 18) & 0x3FFFFu) - 3u)], 1u);
+                        atomicAdd(&hist[89 + (u32)kzg_highbit(mine)], 1u);
+                    }
                 }
             }
         }
+        __syncwarp();
+        // ---- the tables of this block: modes, descriptions, encoding tables (serial, on one lane)
+        if (lane == 0) p = kzg_enc_prepare_tables(T, nseq, hist, ts, s_scr[warp], p, limit);
+        p = reinterpret_cast<u8*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)p, 0));
+        if (!p) continue;                                        // no room: stays a raw block
         __syncwarp();
         // ---- backward: batches of at most 32 sequences inside one part, lane j <-> sequence hi - 1 - j (the order
         // they are written in)
@@ -767,24 +909,28 @@ __global__ void __launch_bounds__(KZG_ENC_EWARPS * 32) kzg_enc_encode_kernel(Kzg
                 syms[lane] = cl; syms[32 + lane] = cm; syms[64 + lane] = co;
                 __syncwarp();
                 if (lane < 3) {
-                    const u16* st = lane == 0 ? s_tab.st_ll : (lane == 1 ? s_tab.st_ml : s_tab.st_of);
-                    const uint2* dd = s_delta + (lane == 0 ? 0 : (lane == 1 ? 36 : 89));
+                    const u16* st = ts.st + KZG_ENC_ST_OFF(lane);
+                    const u32* dnb = ts.dnb + KZG_ENC_SYM_OFF(lane);
+                    const i32* dfs = ts.dfs + KZG_ENC_SYM_OFF(lane);
                     const u32* my = syms + 32 * lane;
                     u32* res = chain + 32 * lane;
                     u32 value = lane == 0 ? stLL : (lane == 1 ? stML : stOF);
                     u32 j = 0;
                     if (first) {                               // the very last sequence initialises the states
-                        const uint2 d = dd[my[0]];
-                        const u32 nb = (d.x + (1u << 15)) >> 16;
-                        value = st[(i32)(((nb << 16) - d.x) >> nb) + (i32)d.y];
+                        const u32 sym = my[0];
+                        if (ts.log[lane] == 0) value = 1;      // RLE mode: the state carries no bits
+                        else {
+                            const u32 nb = (dnb[sym] + (1u << 15)) >> 16;
+                            value = st[(i32)(((nb << 16) - dnb[sym]) >> nb) + dfs[sym]];
+                        }
                         res[0] = 0;
                         j = 1;
                     }
                     for (; j < cnt; j++) {
-                        const uint2 d = dd[my[j]];
-                        const u32 nb = (value + d.x) >> 16;
+                        const u32 sym = my[j];
+                        const u32 nb = (value + dnb[sym]) >> 16;
                         res[j] = (value & ((1u << nb) - 1u)) | (nb << 16);
-                        value = st[(i32)(value >> nb) + (i32)d.y];
+                        value = st[(i32)(value >> nb) + dfs[sym]];
                     }
                     syms[96 + lane] = value;
                 }
@@ -835,9 +981,9 @@ __global__ void __launch_bounds__(KZG_ENC_EWARPS * 32) kzg_enc_encode_kernel(Kzg
         if (lane == 0) {
             KzgBitW w;
             w.acc = carry_bits; w.nbits = carry_n; w.p = out; w.end = limit; w.ovf = false;
-            kzg_bw_add(w, stML, 6);
-            kzg_bw_add(w, stOF, 5);
-            kzg_bw_add(w, stLL, 6);
+            kzg_bw_add(w, stML, ts.log[1]);
+            kzg_bw_add(w, stOF, ts.log[2]);
+            kzg_bw_add(w, stLL, ts.log[0]);
             kzg_bw_add(w, 1, 1);                                 // end mark
             kzg_bw_flush(w);
             if (w.nbits) { if (w.p < w.end) *w.p = (u8)w.acc; else w.ovf = true; w.p++; }
