@@ -29,6 +29,7 @@
 // ZSTD_decompressStream (kompressor-zstd--nativelib/src/jvmCommonMain/jni/Wrapper.cpp:178).
 #pragma once
 #include "kzg_stages.cuh"
+#include "kzg_huf.cuh"
 
 #define KZG_FSE_PAIRS 2                                     // warp pairs per CTA (one CTA per SM)
 #define KZG_FSE_WARPS (2 * KZG_FSE_PAIRS)
@@ -42,6 +43,11 @@
 #define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
 #define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
+// One more warp rides along in every CTA and decodes Huffman literals (kzg_huf_warp_loop) in the shared memory and
+// the issue slots the four sequence warps leave free; it stops taking work when both pairs of its CTA are done.
+#define KZG_FSE_THREADS (KZG_FSE_WARPS * 32 + 64)           // warp 4 is empty: warp 5 shares a scheduler with a post warp, not a chain warp
+#define KZG_FSE_SMEM_TOTAL (KZG_FSE_SMEM + KZG_HUF_WARP_SMEM)
+#define KZG_FSE_DONE_WORD 127                               // in the code-word area: pairs of this CTA that have finished
 #ifndef KZG_FSE_WIDE_LIMIT
 #define KZG_FSE_WIDE_LIMIT 32u                              // most extra bits per sequence the fast loop extracts (tests lower it)
 #endif
@@ -171,7 +177,7 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
 
 // Queue entry of one sequence of one lane (32 bytes): {hi, lo, pLL, pML} + {ofc}.
 //   hi:lo  64-bit window at the sequence's bit position        pLL / pML  packed code entries (bits << 24 | base)
-__global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch B) {
+__global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B) {
     using namespace kzg_fse;
     extern __shared__ uint4 smem4[];
     u32* llx = reinterpret_cast<u32*>(smem4);
@@ -180,6 +186,13 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
     const bool chain = (warp & 1u) == 0;                   // even warp: chain, odd warp: post
     for (u32 k = threadIdx.x; k < KZG_FSE_CODE_WORDS; k += blockDim.x) llx[k] = k < 89 ? B.code_tables[k] : 0u;
     __syncthreads();
+    if (warp == KZG_FSE_WARPS) return;
+    if (warp > KZG_FSE_WARPS) {                             // the literal warp
+        // only where the sequence work lasts long enough to hide a ticket (8 blocks of literals) behind it
+        if (B.ctr->seq_used < (u64)B.ctr->n_sblocks * 1024u) return;
+        kzg_huf_warp_loop(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_SMEM, lane, reinterpret_cast<volatile u32*>(llx + KZG_FSE_DONE_WORD), KZG_FSE_PAIRS);
+        return;
+    }
     const u32 s_llx = smem_addr(llx), s_mlx = s_llx + 36 * 4;
     const u32 s_pair = s_llx + KZG_FSE_CODE_WORDS * 4 + pair * KZG_FSE_PAIR_SMEM;
     const u32 s_tab = s_pair + (lane << 1);
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(KZG_FSE_WARPS * 32, 1) kzg_fse_kernel(KzgBatch
         if (chain && lane == 0) sts32(s_misc, atomicAdd(&B.ctr->ticket_fse, 1u));
         bar_sync(BAR_PAIR);
         const u32 g = lds32(s_misc);
-        if (g * 32 >= n) break;
+        if (g * 32 >= n) { if (chain && lane == 0) atomicAdd(llx + KZG_FSE_DONE_WORD, 1u); break; }
         const u32 si = g * 32 + lane;
         KzgCBlock* cb = nullptr;
         Job j;

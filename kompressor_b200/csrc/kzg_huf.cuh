@@ -38,12 +38,12 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 
 }  // namespace kzg_huf
 
-__global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B) {
+// The work loop of one warp (wbase: its KZG_HUF_WARP_SMEM bytes of shared memory).  With `stop` set, the warp takes no
+// new ticket once *stop reaches stop_at: that is how the warp that rides along in the sequence kernel (kzg_fse.cuh)
+// leaves when the sequence work of its SM is done; kzg_huf_kernel then finishes what is left.
+__device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, u32 lane, const volatile u32* stop, u32 stop_at) {
     using namespace kzg_huf;
-    extern __shared__ uint4 smem4[];
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 hb = lane >> 2, st = lane & 3;
-    u8* wbase = reinterpret_cast<u8*>(smem4) + warp * KZG_HUF_WARP_SMEM;
     u16* tab = reinterpret_cast<u16*>(wbase + hb * KZG_HUF_TAB_BYTES);
     KzgHufScratch* sc = reinterpret_cast<KzgHufScratch*>(wbase + 8u * KZG_HUF_TAB_BYTES + hb * 512u);   // = the block's four rings
     const u32 s_tab = (u32)__cvta_generic_to_shared(tab);
@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
     if (B.ctr->overflow & 3u) return;
     const u32 n = B.ctr->n_hblocks;
     for (;;) {
-        u32 g = 0;
-        if (lane == 0) g = atomicAdd(&B.ctr->ticket_huf, 1u);
+        u32 g = 0xFFFFFFFFu;
+        if (lane == 0 && !(stop && *stop >= stop_at)) g = atomicAdd(&B.ctr->ticket_huf, 1u);
         g = __shfl_sync(0xFFFFFFFFu, g, 0);
-        if (g * 8 >= n) break;
+        if (g == 0xFFFFFFFFu || (u64)g * 8 >= n) break;
         const u32 h = g * 8 + hb;
         bool valid = h < n;
         KzgCBlock* cb = nullptr;
@@ -202,4 +202,10 @@ __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B)
         if (mine && (bad || P != lowbits)) cb->status_lit = KZG_E_CORRUPTION;     // every stream must be consumed exactly
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B) {
+    extern __shared__ uint4 smem4[];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    kzg_huf_warp_loop(B, reinterpret_cast<u8*>(smem4) + warp * KZG_HUF_WARP_SMEM, lane, nullptr, 0);
 }

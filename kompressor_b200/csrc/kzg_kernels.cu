@@ -147,11 +147,11 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
 // ------------------------------------------------------------------------------------------------
 static bool g_attr_done = false;
 
-const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fsetab", "huffman", "fse", "offsets", "bulk", "execute", "execute_runs", "finish" };
+const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fsetab", "fse", "huffman", "offsets", "bulk", "execute", "execute_runs", "finish" };
 
 int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
     const size_t huf_smem = KZG_HUF_SMEM;
-    const size_t fse_smem = KZG_FSE_SMEM;
+    const size_t fse_smem = KZG_FSE_SMEM_TOTAL;
     const size_t exec_smem = KZG_EX_SMEM;
     if (!g_attr_done) {
         cudaFuncSetAttribute(kzg_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem);
@@ -175,9 +175,9 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
     KZG_MARK();
     kzg_fsetab_kernel<<<sm_count * 8, KZG_TAB_WARPS * 32, 0, stream>>>(b);
     KZG_MARK();
-    kzg_huf_kernel<<<sm_count * 3, KZG_HUF_WARPS * 32, huf_smem, stream>>>(b);
+    kzg_fse_kernel<<<sm_count, KZG_FSE_THREADS, fse_smem, stream>>>(b);          // sequences, and literals on the side
     KZG_MARK();
-    kzg_fse_kernel<<<sm_count, KZG_FSE_WARPS * 32, fse_smem, stream>>>(b);
+    kzg_huf_kernel<<<sm_count * 3, KZG_HUF_WARPS * 32, huf_smem, stream>>>(b);     // the literals that are left
     KZG_MARK();
     kzg_offsets_kernel<<<fgrid, 128, 0, stream>>>(b);
     KZG_MARK();
