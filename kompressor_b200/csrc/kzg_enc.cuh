@@ -5,8 +5,7 @@
 // encoder is interchangeable with it, because decoders only see the format (RFC 8878).
 // Parity bar for this side: libzstd 1.5.7 decodes every emitted frame to the original bytes.
 //
-// Format choices of this version: one compressed block per frame, Huffman-coded literals (4 streams, direct weight
-// table, so symbols up to 128; raw literals otherwise), sequence tables made for the block (FSE mode; RLE mode for a
+// Format choices of this version: one compressed block per frame, Huffman-coded literals (4 streams), sequence tables made for the block (FSE mode; RLE mode for a
 // single code; the predefined tables for short blocks, Appendix A.6), repeat-offset codes, optional XXH64 trailer;
 // a raw block when that is not smaller.
 //   match    CTA per chunk, the chunk staged in shared memory: each of the eight warps parses one eighth greedily with
@@ -14,8 +13,9 @@
 //            candidates come from anywhere before): 32 positions probed per step, the first hit extended 128 bytes
 //            per step by the whole warp; then the warps gather the literal runs from shared memory to their final
 //            place in the frame
-//   literals CTA per chunk: histogram, length-limited Huffman code (11 bits), then the four streams in parallel, one
-//            warp each, 128 symbols per step at prefix-summed bit offsets; raw or RLE literals when that is smaller
+//   literals CTA per chunk: histogram, length-limited Huffman code (11 bits), tree description (FSE-coded weights or
+//            the direct form), then the four streams in parallel, one warp each, 128 symbols per step at
+//            prefix-summed bit offsets; raw or RLE literals when that is smaller
 //   encode   warp per chunk: offsets -> repeat codes (forward, serial on one lane over coalesced loads), then the
 //            backward FSE bitstream 32 sequences at a time: three lanes run the three state chains, every lane
 //            assembles its sequence's bit fields at a prefix-summed bit offset in shared memory
@@ -269,6 +269,56 @@ KZG_HD u8* kzg_enc_prepare_tables(const KzgEncTables* T, u32 nseq, const u32* hi
     }
     *modes_byte = (u8)((mode[0] << 6) | (mode[2] << 4) | (mode[1] << 2));     // LL, OF, ML
     return p;
+}
+
+// FSE-coded Huffman weights (Appendix A.4, tree description with a header byte < 128): n weights (the last symbol's
+// is implicit and not part of them), alphabet 0..12, accuracy log 5 or 6, two interleaved states.  Writes the table
+// description and the bitstream to out (not the header byte); returns their size, or 0 when that does not work out
+// (a single distinct weight, no room): the caller then falls back to the direct 4-bit form.
+struct KzgEncWeightScratch { u16 st[64]; u32 dnb[16]; i32 dfs[16]; u32 cnt[16]; KzgEncTabScratch tab; };
+KZG_HD u32 kzg_enc_compress_weights(const u8* w, u32 n, u8* out, u32 cap, KzgEncWeightScratch& sc) {
+    if (n < 2) return 0;
+    u32 maxw = 0, distinct = 0;
+    for (u32 k = 0; k < 16; k++) sc.cnt[k] = 0;
+    for (u32 k = 0; k < n; k++) { sc.cnt[w[k]]++; if (w[k] > maxw) maxw = w[k]; }
+    for (u32 k = 0; k <= maxw; k++) distinct += sc.cnt[k] != 0;
+    if (distinct < 2) return 0;
+    u32 log = 6;
+    const u32 src_bits = (u32)kzg_highbit(n - 1) < 2 ? 0 : (u32)kzg_highbit(n - 1) - 2;
+    if (src_bits < log) log = src_bits;
+    u32 min_bits = (u32)kzg_highbit(n) + 1;
+    if (maxw && (u32)kzg_highbit(maxw) + 2 < min_bits) min_bits = (u32)kzg_highbit(maxw) + 2;
+    if (log < min_bits) log = min_bits;
+    if (log < 5) log = 5;
+    if (log > 6) return 0;
+    kzg_enc_normalize(sc.cnt, maxw + 1, n, log, sc.tab.norm);
+    const u32 hsz = kzg_enc_write_ncount(out, cap, sc.tab.norm, maxw + 1, log);
+    if (hsz == 0) return 0;
+    kzg_enc_build_ctable(sc.tab.norm, maxw + 1, log, sc.st, sc.dnb, sc.dfs, sc.tab.cumul, sc.tab.symbol_of);
+    KzgBitW bw;
+    bw.acc = 0; bw.nbits = 0; bw.p = out + hsz; bw.end = out + cap; bw.ovf = false;
+    KzgFseC s1, s2;                                          // state 1 carries the even positions, state 2 the odd ones
+    u32 k = n;
+    if (n & 1) {
+        kzg_fsec_init(s1, sc.st, sc.dnb, sc.dfs, w[--k]);
+        kzg_fsec_init(s2, sc.st, sc.dnb, sc.dfs, w[--k]);
+        kzg_fsec_encode(bw, s1, sc.st, sc.dnb, sc.dfs, w[--k]);
+        kzg_bw_flush(bw);
+    } else {
+        kzg_fsec_init(s2, sc.st, sc.dnb, sc.dfs, w[--k]);
+        kzg_fsec_init(s1, sc.st, sc.dnb, sc.dfs, w[--k]);
+    }
+    while (k > 0) {
+        kzg_fsec_encode(bw, s2, sc.st, sc.dnb, sc.dfs, w[--k]);
+        kzg_fsec_encode(bw, s1, sc.st, sc.dnb, sc.dfs, w[--k]);
+        kzg_bw_flush(bw);
+    }
+    kzg_bw_add(bw, s2.value, log);
+    kzg_bw_add(bw, s1.value, log);
+    kzg_bw_add(bw, 1, 1);                                    // end mark
+    kzg_bw_flush(bw);
+    if (bw.nbits) { if (bw.p < bw.end) *bw.p = (u8)bw.acc; else bw.ovf = true; bw.p++; }
+    return bw.ovf ? 0u : (u32)(bw.p - out);
 }
 
 // Repeat-offset code of a distance (Appendix A.7); updates the history like the decoder will.
@@ -630,6 +680,8 @@ __global__ void __launch_bounds__(KZG_ENC_HUF_THREADS) kzg_enc_literals_kernel(K
     __shared__ u8 len[256];                        // code length per symbol, 0 = absent
     __shared__ u16 code[256];
     __shared__ u32 stage[4][48];                   // per stream: 128 symbols x 11 bits + carry
+    __shared__ KzgEncWeightScratch wsc;            // FSE-coded weight table (thread 0)
+    __shared__ u8 wts[256], wbuf[128];
     __shared__ u32 misc[16];                       // [0] ticket, [1] max symbol, [2] mode, [3] maxbits, [4..8) stream bits, [8..12) stream offsets, [12] header bytes
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
@@ -665,7 +717,7 @@ __global__ void __launch_bounds__(KZG_ENC_HUF_THREADS) kzg_enc_literals_kernel(K
         const u32 maxsym = misc[1];
         // mode: 0 raw, 1 RLE, 2 Huffman
         u32 mode = 2;
-        if (nl < 64 || maxsym > 128) mode = 0;
+        if (nl < 64) mode = 0;
         if (m == 1 && nl > 0) mode = 1;
         if (mode == 2) {
             // ---- present symbols by ascending count (rank sort), then the Huffman tree on one thread
@@ -737,21 +789,29 @@ __global__ void __launch_bounds__(KZG_ENC_HUF_THREADS) kzg_enc_literals_kernel(K
             }
             __syncthreads();
             if (tid == 0) {
-                const u32 whdr = 1 + ((maxsym + 1) >> 1);               // header byte + maxsym weights, two per byte
+                // tree description: the weights of symbols 0 .. maxsym-1 (the last one is implicit), FSE-coded when
+                // that is smaller or when there are more than 128 of them, else two per byte
+                for (u32 k = 0; k < maxsym; k++) wts[k] = len[k] ? (u8)(maxbits + 1 - len[k]) : (u8)0;
+                const u32 direct = 1 + ((maxsym + 1) >> 1);
+                const u32 fsz = kzg_enc_compress_weights(wts, maxsym, wbuf, 127, wsc);
+                const bool coded = fsz != 0 && (maxsym > 128 || 1 + fsz < direct);
+                const u32 whdr = coded ? 1 + fsz : direct;
                 const u32 sz0 = (misc[4] + 8) >> 3, sz1 = (misc[5] + 8) >> 3, sz2 = (misc[6] + 8) >> 3, sz3 = (misc[7] + 8) >> 3;
                 const u32 csize = whdr + 6 + sz0 + sz1 + sz2 + sz3;
                 const u32 big = nl > csize ? nl : csize;
                 const u32 fmt = big < 1024 ? 1u : (big < 16384 ? 2u : 3u), lhdr = 2 + fmt, fbits = fmt == 1 ? 10u : (fmt == 2 ? 14u : 18u);
-                if (lhdr + csize >= 3 + nl || sz0 > 65535 || sz1 > 65535 || sz2 > 65535) misc[2] = 0;      // raw is not larger
+                if (lhdr + csize >= 3 + nl || sz0 > 65535 || sz1 > 65535 || sz2 > 65535 || (!coded && maxsym > 128)) misc[2] = 0;      // raw is not larger
                 else {
                     misc[2] = 2;
                     const u64 h = 2ull | ((u64)fmt << 2) | ((u64)nl << 4) | ((u64)csize << (4 + fbits));
                     for (u32 k = 0; k < lhdr; k++) blk[k] = (u8)(h >> (8 * k));
                     u8* p = blk + lhdr;
-                    *p++ = (u8)(127 + maxsym);
-                    for (u32 k = 0; k < maxsym; k += 2) {
-                        const u32 w0 = len[k] ? maxbits + 1 - len[k] : 0u, w1 = (k + 1 < maxsym && len[k + 1]) ? maxbits + 1 - len[k + 1] : 0u;
-                        *p++ = (u8)((w0 << 4) | w1);
+                    if (coded) {
+                        *p++ = (u8)fsz;
+                        for (u32 k = 0; k < fsz; k++) *p++ = wbuf[k];
+                    } else {
+                        *p++ = (u8)(127 + maxsym);
+                        for (u32 k = 0; k < maxsym; k += 2) *p++ = (u8)((wts[k] << 4) | (k + 1 < maxsym ? wts[k + 1] : 0));
                     }
                     kzg_wr16(p, sz0); kzg_wr16(p + 2, sz1); kzg_wr16(p + 4, sz2);
                     const u32 base = lhdr + whdr + 6;

@@ -74,3 +74,13 @@ def compress(chunks, checksum=False):
                                 caps.ctypes.data, 1 if checksum else 0, status.ctypes.data, osz.ctypes.data)
     assert r == 0, r
     return [bytes(dst[int(doffs[i]):int(doffs[i] + osz[i])]) for i in range(n)], status
+
+
+def weights_roundtrip(weights) -> int:
+    """Encoder's FSE-coded Huffman weight description -> decoder's parser. Returns the size (0: declined), -1: mismatch."""
+    global _lib
+    if _lib is None:
+        run([], [])
+    w = np.asarray(weights, dtype=np.uint8)
+    _lib.kzs_weights_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+    return int(_lib.kzs_weights_roundtrip(w.ctypes.data, w.size))

@@ -200,3 +200,19 @@ extern "C" int kzs_compress_batch(const u8* src, const u64* src_off, const u64* 
     }
     return 0;
 }
+
+// FSE-coded Huffman weights: the encoder's description of `n` weights (the last symbol's implicit one is recomputed by
+// the reader), read back by the decoder's own parser.  Returns the description size (0: encoder declined), -1 on mismatch.
+extern "C" int kzs_weights_roundtrip(const u8* w, u32 n) {
+    u8 buf[300];
+    KzgEncWeightScratch sc;
+    const u32 sz = kzg_enc_compress_weights(w, n, buf + 1, 127, sc);
+    if (sz == 0 || sz >= 128) return 0;
+    buf[0] = (u8)sz;
+    u8 back[260];
+    u32 nsym = 0, maxbits = 0;
+    const u32 used = kzg_read_huf_weights(buf, 1 + sz, back, nsym, maxbits);
+    if (used != 1 + sz || nsym != n + 1) return -1;
+    for (u32 k = 0; k < n; k++) if (back[k] != w[k]) return -1;
+    return (int)sz;
+}

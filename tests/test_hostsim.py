@@ -75,3 +75,33 @@ def test_encode_stage_roundtrip_through_libzstd(libzstd):
             assert err == 0 and out == c
     assert hostsim.compress([b""])[0][0].hex() == "28b52ffd2000010000"
     assert len(hostsim.compress([chunks[0]])[0][0]) < 0.4 * 65536
+
+
+def test_fse_coded_huffman_weights_roundtrip():
+    """Compress side: the encoder's FSE-coded tree description (kzg_enc_compress_weights) read back by the decoder's
+    parser (kzg_read_huf_weights) for random complete codes of up to 256 symbols and 11 bits."""
+    rng = np.random.default_rng(3)
+    checked = 0
+    for _ in range(300):
+        m = int(rng.integers(2, 257))
+        leaves = [0]
+        while len(leaves) < m:
+            cands = [j for j, x in enumerate(leaves) if x < 11]
+            if not cands:
+                break
+            i = cands[int(rng.integers(0, len(cands)))]
+            leaves[i] += 1
+            leaves.append(leaves[i])
+        m = len(leaves)
+        maxbits = max(leaves)
+        nsym = int(rng.integers(m, 257))
+        syms = np.unique(np.append(rng.choice(nsym - 1, m - 1, replace=False), nsym - 1)) if m > 1 else np.array([nsym - 1])
+        if len(syms) != m:
+            continue
+        w = np.zeros(nsym, np.uint8)
+        for s_, l in zip(syms, rng.permutation(np.array(leaves))):
+            w[s_] = maxbits + 1 - l
+        r = hostsim.weights_roundtrip(w[:-1])
+        assert r >= 0
+        checked += r > 0
+    assert checked > 200
