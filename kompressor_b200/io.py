@@ -193,8 +193,86 @@ class SliceTransformRawSource:
         self.closed = True
 
 
-def pipe(source, transform: SliceTransform) -> SliceTransformRawSource:
-    """RawSource.pipe(transform): RawSource"""
+class BufferSink:
+    """RawSink that collects what is written to it (kotlinx-io: a Buffer used as a Sink)."""
+
+    def __init__(self):
+        self.buffer = Buffer()
+        self.closed = False
+
+    def write(self, source: Buffer, byteCount: int) -> None:
+        source.readAtMostTo(self.buffer, byteCount)
+
+    def flush(self) -> None:
+        pass
+
+    def close(self) -> None:
+        self.closed = True
+
+    def readByteArray(self) -> bytes:
+        return self.buffer.readByteArray()
+
+
+class SliceTransformRawSink:
+    """SliceTransform.pipe(RawSink): RawSink (SliceTransformRawSink.kt:10-47).  What the transform produces goes to the
+    downstream sink segment by segment; close() finishes the transform (finishInto, BufferSliceTransformHelper.kt:49-55)."""
+
+    def __init__(self, transform: SliceTransform, rawSink):
+        self.sink = rawSink
+        self.helper = BufferSliceTransformHelper(transform)
+        self.closed = False
+
+    def _drain(self, staged: Buffer) -> None:
+        if staged.size:
+            self.sink.write(staged, staged.size)
+
+    def write(self, source: Buffer, byteCount: int) -> None:
+        if self.closed:
+            raise RuntimeError("Sink is closed")
+        if byteCount <= 0:
+            return
+        bytesRead = 0
+        while bytesRead < byteCount:
+            staged = Buffer()                         # sink.writeToInternalBufferReturning { ... }
+            bytesRead += self.helper.transform(source, BufferTracker(staged), byteCount - bytesRead, False)
+            self._drain(staged)
+
+    def flush(self) -> None:
+        if self.closed:
+            raise RuntimeError("Sink is closed")
+        self.sink.flush()
+
+    def close(self) -> None:
+        if self.closed:
+            return
+        while True:                                   # finishInto: consume until the transform has nothing left
+            staged = Buffer()
+            tracker = BufferTracker(staged)
+            _transform_into_tracker(self.helper.transform_, self.helper.inputBuffer, tracker, True)
+            self._drain(staged)
+            if not tracker.insufficient:
+                break
+        if self.helper.inputBuffer.insufficient:
+            raise RuntimeError("Insufficient data in input buffer")
+        if self.helper.inputBuffer.hasData:
+            raise RuntimeError("Input buffer was not fully consumed after close()")
+        self.closed = True
+        self.sink.close()
+
+
+def transferTo(data, sink) -> int:
+    """Source.transferTo(sink) for bytes: everything is written through 8 KiB segments."""
+    buf = Buffer(bytes(data))
+    n = buf.size
+    while buf.size:
+        sink.write(buf, min(buf.size, SEGMENT_SIZE))
+    return n
+
+
+def pipe(source, transform):
+    """RawSource.pipe(transform): RawSource  (source first)  /  SliceTransform.pipe(sink): RawSink  (transform first)."""
+    if isinstance(source, SliceTransform):
+        return SliceTransformRawSink(source, transform)
     if isinstance(source, (bytes, bytearray, memoryview)):
         source = BytesSource(source)
     return SliceTransformRawSource(source, transform)

@@ -217,3 +217,21 @@ def test_compressor_parameters_and_dictionaries(api, libzstd):
     with pytest.raises(zstd.IllegalStateException) as ei:
         zstd.ZstdCompressor(dictionary=trained)
     assert ei.value.code == 40
+
+
+def test_sampleRoundtripKotlinxIoSink(api, libzstd):    # ZstdTest.kt:40-47: compressor.pipe(decompressor.pipe(output))
+    import corpus
+    _, io, zstd = api
+    for data in (np.random.default_rng(21).integers(0, 256, 1024 * 1024 + 3, dtype=np.uint8).tobytes(),
+                 bytes(corpus.generate("json", 22, 700001))):
+        output = io.BufferSink()
+        sink = io.pipe(zstd.ZstdCompressor(compressionLevel=3), io.pipe(zstd.ZstdDecompressor(), output))
+        io.transferTo(data, sink)
+        sink.close()
+        assert output.closed and output.readByteArray() == data
+        # the decompressor alone behind a sink, fed with libzstd's frame
+        output = io.BufferSink()
+        sink = io.pipe(zstd.ZstdDecompressor(), output)
+        io.transferTo(libzstd.compress(data, 3, checksum=True), sink)
+        sink.close()
+        assert output.readByteArray() == data

@@ -66,3 +66,23 @@ def test_pipe_small_reads():
             break
         got += out.readByteArray()
     assert got == EXPECTED
+
+
+def test_pipe_into_sink():
+    """SliceTransform.pipe(RawSink) (SliceTransformRawSink.kt:10-47): 8 KiB slices in, finish on close()."""
+    from kompressor_b200.io import BufferSink, transferTo
+    t = XorSliceTransform()
+    output = BufferSink()
+    sink = pipe(t, output)
+    assert transferTo(DATA, sink) == len(DATA)
+    sink.close()
+    assert output.closed and output.readByteArray() == EXPECTED
+    assert max(c[0] for c in t.calls) <= 8192 and t.calls[-1][2] is True      # the last call is the finishing one
+    with pytest.raises(RuntimeError):
+        sink.write(Buffer(b"x"), 1)
+    # two transforms chained through sinks
+    output = BufferSink()
+    sink = pipe(XorSliceTransform(), pipe(XorSliceTransform(), output))
+    transferTo(DATA, sink)
+    sink.close()
+    assert output.readByteArray() == DATA
