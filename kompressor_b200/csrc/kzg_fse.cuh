@@ -269,7 +269,10 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             cp_commit();
             cp_wait<0>();
             ready_lo = pend1 = pend2 = next_c + 1;
-            P = j.P0;
+            // Lanes without a block keep executing the loop on a frozen position: give each its own ring word, or all of
+            // them read the same bank of their (128-byte strided) rings three times per sequence -- a 32-way conflict
+            // that doubles the time of a group with few blocks (small batches).
+            P = nseq ? j.P0 : (i32)(lane << 5);
         }
 
         // 64-bit window [P-64, P) -> hi:lo from the lane's ring (word w of the stream sits at (w & 31) * 4)

@@ -79,7 +79,8 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         const u8* base = nullptr;
         u8* dst = nullptr;
         u32 cnt = 0;
-        i32 P = 0, lowbits = 0, next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
+        // (lanes without a stream run the loops on a frozen position: one ring word each, or they all hit the same bank)
+        i32 P = (i32)(lane << 5), lowbits = 0, next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
         bool mine = valid && st < cb->n_streams, bad = false;
         if (mine) {
             const u32 regen = cb->lit_regen;
