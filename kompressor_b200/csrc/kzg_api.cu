@@ -140,7 +140,7 @@ extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
              cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); kzg_ctx_destroy(c); return (int)KZG_E_MEMORY; }
     // constants: default FSE descriptor + packed code tables
-    static KzgConsts hc;
+    KzgConsts hc;
     memset(&hc, 0, sizeof hc);
     kzg_default_fse_desc(hc.def);
     kzg_code_tables(hc.codes, hc.codes + 36);
@@ -184,8 +184,8 @@ extern "C" int kzg_ctx_set_dictionary(kzg_ctx* c, const void* dict, size_t size)
     const u8* const end = p + size;
     u32 id = 0, entropy = 0, rep[3] = { 1, 4, 8 };
     if (size >= 8 && kzg_rd32(p) == KZG_DICT_MAGIC) {
-        static KzgFseDesc fd;
-        static KzgHufDesc hd;
+        KzgFseDesc fd;                       // (on the stack: contexts load dictionaries concurrently)
+        KzgHufDesc hd;
         memset(&fd, 0, sizeof fd);
         memset(&hd, 0, sizeof hd);
         id = kzg_rd32(p + 4);

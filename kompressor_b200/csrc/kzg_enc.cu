@@ -59,7 +59,7 @@ extern "C" int kzg_enc_create(kzg_enc** out, int device) {
     e->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
     for (int k = 0; k < 5; k++) cudaEventCreate(&e->ev[k]);
-    static KzgEncTables host_tables;
+    KzgEncTables host_tables;
     kzg_enc_build_tables(host_tables);
     if (e->tables.ensure(sizeof(KzgEncTables)) || e->tickets.ensure(64) ||
         cudaMemcpy(e->tables.p, &host_tables, sizeof host_tables, cudaMemcpyHostToDevice) != cudaSuccess) {
