@@ -121,7 +121,7 @@ static int enqueue(kzg_enc* e, const void* d_src, const uint64_t* d_src_off, con
     if (prof) cudaEventRecord(e->ev[1], s);
     kzg_enc_literals_kernel<<<e->sm_count * 8, KZG_ENC_HUF_THREADS, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[2], s);
-    kzg_enc_encode_kernel<<<e->sm_count * 4, KZG_ENC_EWARPS * 32, 0, s>>>(B);
+    kzg_enc_encode_kernel<<<e->sm_count * 8, KZG_ENC_EWARPS * 32, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[3], s);
     kzg_enc_finish_kernel<<<e->sm_count * 8, 128, 0, s>>>(B);
     if (prof) cudaEventRecord(e->ev[4], s);

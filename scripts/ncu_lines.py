@@ -10,8 +10,13 @@ div = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "kompressor_b200", "libkzg.so")], cwd=tmp, capture_output=True)
-cubin = os.path.join(tmp, "kzg_kernels.sm_100a.cubin")
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+dis = ""
+for f in sorted(os.listdir(tmp)):                 # the cubin that holds the kernel
+    if f.endswith(".cubin"):
+        d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if ".text." + kern in d:
+            dis = d
+            break
 line_of = {}
 cur, infn = None, False
 for ln in dis.splitlines():
@@ -27,7 +32,7 @@ for ln in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
     if m:
         line_of[int(m.group(1), 16)] = cur
-base_name = re.split(r"IL|Ev8KzgBatch|8KzgBatch", re.sub(r"^_Z\d+", "", kern))[0]      # ncu matches the un-templated name
+base_name = re.split(r"IL|Ev8KzgBatch|8KzgBatch|11KzgEncBatch", re.sub(r"^_Z\d+", "", kern))[0]      # ncu matches the un-templated name
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", base_name, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
