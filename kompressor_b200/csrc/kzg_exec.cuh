@@ -88,11 +88,16 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 f
     if (fill) {
         for (; d != dend; d += 4) sts32(d, w0);
     } else {
-        for (; d != dend; d += 4) {
-            A += 4;
-            const u32 hi = lds32(A);
-            sts32(d, __funnelshift_r(lo, hi, r));
-            lo = hi;
+        // two words per trip (the second one predicated): fewer compares and branches per byte
+        for (; d != dend; d += 8) {
+            const u32 h1 = lds32(A + 4);
+            const bool two = d + 4 != dend;
+            sts32(d, __funnelshift_r(lo, h1, r));
+            if (!two) { A += 4; lo = h1; d += 4; break; }
+            const u32 h2 = lds32(A + 8);
+            sts32(d + 4, __funnelshift_r(h1, h2, r));
+            A += 8;
+            lo = h2;
         }
     }
     const u32 t = n & 3u;
