@@ -88,16 +88,29 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 f
     if (fill) {
         for (; d != dend; d += 4) sts32(d, w0);
     } else {
-        // two words per trip (the second one predicated): fewer compares and branches per byte
-        for (; d != dend; d += 8) {
+        // up to four words per trip (the later ones predicated): fewer compares and branches per byte, and the loads
+        // of a trip are independent of each other
+        for (u32 rem = n >> 2; rem;) {
             const u32 h1 = lds32(A + 4);
-            const bool two = d + 4 != dend;
             sts32(d, __funnelshift_r(lo, h1, r));
-            if (!two) { A += 4; lo = h1; d += 4; break; }
-            const u32 h2 = lds32(A + 8);
-            sts32(d + 4, __funnelshift_r(h1, h2, r));
-            A += 8;
-            lo = h2;
+            lo = h1;
+            if (rem > 1) {
+                const u32 h2 = lds32(A + 8);
+                sts32(d + 4, __funnelshift_r(h1, h2, r));
+                lo = h2;
+                if (rem > 2) {
+                    const u32 h3 = lds32(A + 12);
+                    sts32(d + 8, __funnelshift_r(h2, h3, r));
+                    lo = h3;
+                    if (rem > 3) {
+                        const u32 h4 = lds32(A + 16);
+                        sts32(d + 12, __funnelshift_r(h3, h4, r));
+                        lo = h4;
+                    }
+                }
+            }
+            const u32 done = min(rem, 4u);
+            A += done << 2; d += done << 2; rem -= done;
         }
     }
     const u32 t = n & 3u;
