@@ -39,6 +39,14 @@ namespace kzg_ex {
 __device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// predicated forms: one instruction, no branch around it (a false predicate leaves `v` as passed in)
+__device__ __forceinline__ u32 lds32_if(bool p, u32 a, u32 v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}" : "+r"(v) : "r"(a), "r"((u32)p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32_if(bool p, u32 a, u32 v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" :: "r"(a), "r"(v), "r"((u32)p) : "memory");
+}
 __device__ __forceinline__ void sts8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds128(u32 a) {
     uint4 v;
@@ -91,24 +99,17 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 f
         // up to four words per trip (the later ones predicated): fewer compares and branches per byte, and the loads
         // of a trip are independent of each other
         for (u32 rem = n >> 2; rem;) {
+            const bool p2 = rem > 1, p3 = rem > 2, p4 = rem > 3;
+            // (loads and stores alternate: a source 8 bytes behind its destination reads what this trip has written)
             const u32 h1 = lds32(A + 4);
             sts32(d, __funnelshift_r(lo, h1, r));
-            lo = h1;
-            if (rem > 1) {
-                const u32 h2 = lds32(A + 8);
-                sts32(d + 4, __funnelshift_r(h1, h2, r));
-                lo = h2;
-                if (rem > 2) {
-                    const u32 h3 = lds32(A + 12);
-                    sts32(d + 8, __funnelshift_r(h2, h3, r));
-                    lo = h3;
-                    if (rem > 3) {
-                        const u32 h4 = lds32(A + 16);
-                        sts32(d + 12, __funnelshift_r(h3, h4, r));
-                        lo = h4;
-                    }
-                }
-            }
+            const u32 h2 = lds32_if(p2, A + 8, 0u);
+            sts32_if(p2, d + 4, __funnelshift_r(h1, h2, r));
+            const u32 h3 = lds32_if(p3, A + 12, 0u);
+            sts32_if(p3, d + 8, __funnelshift_r(h2, h3, r));
+            const u32 h4 = lds32_if(p4, A + 16, 0u);
+            sts32_if(p4, d + 12, __funnelshift_r(h3, h4, r));
+            lo = p4 ? h4 : (p3 ? h3 : (p2 ? h2 : h1));
             const u32 done = min(rem, 4u);
             A += done << 2; d += done << 2; rem -= done;
         }
