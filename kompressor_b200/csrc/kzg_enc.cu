@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define KZG_ENC_MAX_SUB 32                    // host-pointer API: sub-batches pipelined over the copy engines
+#define KZG_ENC_SUB_BYTES (128ull << 20)      // input bytes per sub-batch
+
 namespace {
 struct Buf {
     void* p = nullptr;
@@ -31,7 +34,8 @@ struct kzg_enc {
     int device = 0;
     int sm_count = 0;
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, in_stream = nullptr, out_stream = nullptr;     // kernels; H2D; D2H of the host-pointer API
+    cudaEvent_t ev_in[KZG_ENC_MAX_SUB], ev_cmp[KZG_ENC_MAX_SUB];
     Buf tables, seq, chunks, tickets, lit;       // workspace
     Buf st_src, st_dst, st_tab;                  // staging of the host-pointer API
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
@@ -57,8 +61,14 @@ extern "C" int kzg_enc_create(kzg_enc** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
     e->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return -(int)KZG_E_MEMORY; }
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->out_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete e; return -(int)KZG_E_MEMORY; }
     for (int k = 0; k < 5; k++) cudaEventCreate(&e->ev[k]);
+    for (int k = 0; k < KZG_ENC_MAX_SUB; k++) {
+        cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_cmp[k], cudaEventDisableTiming);
+    }
     KzgEncTables host_tables;
     kzg_enc_build_tables(host_tables);
     if (e->tables.ensure(sizeof(KzgEncTables)) || e->tickets.ensure(64) ||
@@ -75,7 +85,10 @@ extern "C" void kzg_enc_destroy(kzg_enc* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    if (e->in_stream) cudaStreamDestroy(e->in_stream);
+    if (e->out_stream) cudaStreamDestroy(e->out_stream);
     for (int k = 0; k < 5; k++) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    for (int k = 0; k < KZG_ENC_MAX_SUB; k++) { if (e->ev_in[k]) cudaEventDestroy(e->ev_in[k]); if (e->ev_cmp[k]) cudaEventDestroy(e->ev_cmp[k]); }
     e->tables.release(); e->seq.release(); e->chunks.release(); e->tickets.release(); e->lit.release();
     e->st_src.release(); e->st_dst.release(); e->st_tab.release();
     delete e;
@@ -179,19 +192,62 @@ extern "C" int kzg_compress_batch_host(kzg_enc* e, const void* src, const uint64
         h_tab[i] = src_off[i] - src_lo; h_tab[n + i] = src_size[i];
         h_tab[2 * n + i] = dst_off[i] - dst_lo; h_tab[3 * n + i] = dst_cap[i];
     }
-    cudaStream_t s = e->stream;
-    bool ok = cudaMemcpyAsync(e->st_tab.p, h_tab, n * 4 * 8, cudaMemcpyHostToDevice, s) == cudaSuccess &&
-              cudaMemcpyAsync(e->st_src.p, (const u8*)src + src_lo, src_span, cudaMemcpyHostToDevice, s) == cudaSuccess;
-    int rc = 0;
-    if (ok) {
-        rc = enqueue(e, e->st_src.p, t_off, t_size, e->st_dst.p, t_doff, t_dcap, n, max_chunk, flags, t_status, t_osize, s);
-        ok = rc >= 0 && cudaMemcpyAsync(status, t_status, n * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-             cudaMemcpyAsync(out_size, t_osize, n * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-             cudaStreamSynchronize(s) == cudaSuccess;
+    // Sub-batches of consecutive chunks, pipelined over three streams: while sub-batch k is compressed, the input of
+    // k+1 is on its way in and the frames of k-1 are on their way out.  The kernels of successive sub-batches run
+    // back to back on one stream and share the workspace.
+    u64 bounds[KZG_ENC_MAX_SUB + 1];
+    u64 nsub = 0;
+    bounds[0] = 0;
+    {
+        u64 total_src = 0;
+        for (u64 i = 0; i < n; i++) total_src += src_size[i];
+        u64 goal = KZG_ENC_SUB_BYTES;
+        while (total_src / goal >= KZG_ENC_MAX_SUB) goal <<= 1;
+        u64 acc = 0;
+        for (u64 i = 0; i < n; i++) {
+            acc += src_size[i];
+            if (acc >= goal || i + 1 == n) { bounds[++nsub] = i + 1; acc = 0; }
+        }
     }
-    if (ok) {
-        // copy back either what each frame occupies (sizes are known now) or, when there are many frames, whole
-        // capacity regions with adjacent ones coalesced (one copy per run instead of one per frame)
+    cudaStream_t s = e->stream, s_in = e->in_stream, s_out = e->out_stream;
+    bool ok = cudaMemcpyAsync(e->st_tab.p, h_tab, n * 4 * 8, cudaMemcpyHostToDevice, s_in) == cudaSuccess;
+    int rc = 0;
+    for (u64 k = 0; ok && k < nsub; k++) {
+        const u64 f0 = bounds[k], f1 = bounds[k + 1];
+        u64 lo = ~0ull, hi = 0, mc = 0;
+        for (u64 i = f0; i < f1; i++) {
+            if (src_off[i] < lo) lo = src_off[i];
+            if (src_off[i] + src_size[i] > hi) hi = src_off[i] + src_size[i];
+            if (src_size[i] > mc) mc = src_size[i];
+        }
+        ok = (hi <= lo || cudaMemcpyAsync((u8*)e->st_src.p + (lo - src_lo), (const u8*)src + lo, hi - lo, cudaMemcpyHostToDevice, s_in) == cudaSuccess) &&
+             cudaEventRecord(e->ev_in[k], s_in) == cudaSuccess && cudaStreamWaitEvent(s, e->ev_in[k], 0) == cudaSuccess;
+        if (!ok) break;
+        rc = enqueue(e, e->st_src.p, t_off + f0, t_size + f0, e->st_dst.p, t_doff + f0, t_dcap + f0, f1 - f0, max_chunk, flags,
+                     t_status + f0, t_osize + f0, s);
+        if (rc < 0) break;
+        ok = cudaEventRecord(e->ev_cmp[k], s) == cudaSuccess && cudaStreamWaitEvent(s_out, e->ev_cmp[k], 0) == cudaSuccess;
+        if (nsub > 1) {
+            // frame sizes are not known on the host yet: whole capacity regions, adjacent ones coalesced
+            u64 run_lo = dst_off[f0], run_hi = dst_off[f0] + dst_cap[f0];
+            for (u64 i = f0 + 1; ok && i <= f1; i++) {
+                if (i < f1 && dst_off[i] == run_hi) { run_hi += dst_cap[i]; continue; }
+                if (run_hi > run_lo)
+                    ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)e->st_dst.p + (run_lo - dst_lo), run_hi - run_lo, cudaMemcpyDeviceToHost, s_out) == cudaSuccess;
+                if (i < f1) { run_lo = dst_off[i]; run_hi = dst_off[i] + dst_cap[i]; }
+            }
+        }
+    }
+    // status and sizes once, at the end: the caller's arrays may be pageable, and a copy into pageable memory makes
+    // the host wait for everything enqueued before it
+    if (ok && rc >= 0)
+        ok = cudaMemcpyAsync(status, t_status, n * 4, cudaMemcpyDeviceToHost, s_out) == cudaSuccess &&
+             cudaMemcpyAsync(out_size, t_osize, n * 8, cudaMemcpyDeviceToHost, s_out) == cudaSuccess;
+    const bool synced = cudaStreamSynchronize(s_in) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess && cudaStreamSynchronize(s_out) == cudaSuccess;
+    ok = ok && synced;
+    if (ok && rc >= 0 && nsub == 1) {
+        // one sub-batch: copy back either what each frame occupies (sizes are known now) or, when there are many frames,
+        // whole capacity regions with adjacent ones coalesced (one copy per run instead of one per frame)
         u64 total_out = 0, total_cap = 0;
         for (u64 i = 0; i < n; i++) { total_out += status[i] == 0 ? out_size[i] : 0; total_cap += dst_cap[i]; }
         const bool exact = (double)n * 3e-6 + (double)total_out / 50e9 < (double)total_cap / 50e9;
@@ -201,11 +257,11 @@ extern "C" int kzg_compress_batch_host(kzg_enc* e, const void* src, const uint64
             const u64 len = i < n ? (exact ? (status[i] == 0 ? out_size[i] : 0) : dst_cap[i]) : 0;
             const bool have = i < n && len > 0;
             if (have && open && dst_off[i] == run_hi) { run_hi += len; continue; }
-            if (open) ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)e->st_dst.p + (run_lo - dst_lo), run_hi - run_lo, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            if (open) ok = cudaMemcpyAsync((u8*)dst + run_lo, (const u8*)e->st_dst.p + (run_lo - dst_lo), run_hi - run_lo, cudaMemcpyDeviceToHost, s_out) == cudaSuccess;
             open = have;
             if (have) { run_lo = dst_off[i]; run_hi = dst_off[i] + len; }
         }
-        ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(s_out) == cudaSuccess;
     }
     free(h_tab);
     if (rc < 0) return rc;
