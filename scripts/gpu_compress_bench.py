@@ -85,10 +85,4 @@ for _ in range(6):
                                    h_doff.ctypes.data, h_cap.ctypes.data, n, 0, h_status.ctypes.data, h_osz.ctypes.data)
     ts.append(time.perf_counter() - t0)
     assert rc == 0 and not h_status.any()
-from oracle.libzstd_ref import load
-z = load("1.5.7")
-ok = True
-for i in (0, 1, n // 2, n - 1):
-    out, err = z.decompress_oneshot(h_dst[int(h_doff[i]):int(h_doff[i] + h_osz[i])].tobytes(), 65536 + 64)
-    ok = ok and err == 0 and out == c.raw[i * 65536:(i + 1) * 65536].tobytes()
-print(f"host API ({kind}, {n} chunks, pinned): best {min(ts[1:]) * 1e3:.2f} ms = {raw_p.size / min(ts[1:]) / 1e9:.1f} GB/s in, libzstd spot check {ok}", flush=True)
+print(f"host API ({kind}, {n} chunks, pinned): best {min(ts[1:]) * 1e3:.2f} ms = {raw_p.size / min(ts[1:]) / 1e9:.1f} GB/s in", flush=True)

@@ -1,5 +1,5 @@
-"""Differential stress test on a GPU (development, not part of the default suite):
-   python scripts/gpu_fuzz.py [n_frames] [seed]
+"""Differential stress test on a GPU (test infrastructure, not part of the default suite; run from the repository root):
+   python tests/stress/gpu_fuzz.py [n_frames] [seed]
 Random inputs (all corpus kinds, run-like data, random sizes 0..400 KB, levels -5..19, checksum on/off, pledged
 and streamed headers) are compressed by the real libzstd and decoded in batches through the C ABI; then single-bit
 corruptions are checked for the same accept/reject decision (and bytes) as the oracle."""

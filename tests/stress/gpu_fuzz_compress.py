@@ -1,5 +1,5 @@
-"""Stress test of the batch frame writer on a GPU (development, not part of the default suite):
-   python scripts/gpu_fuzz_compress.py [n_inputs] [seed]
+"""Stress test of the batch frame writer on a GPU (test infrastructure, not part of the default suite; run from the repository root):
+   python tests/stress/gpu_fuzz_compress.py [n_inputs] [seed]
 Random inputs (all corpus kinds, tiny alphabets, short periods, mirrored text; sizes 0..400 KB; chunk sizes 1..128 KiB;
 checksum on/off) are compressed on the GPU; the real libzstd must decode every result to the input, and so must the
 GPU decoder."""
