@@ -28,6 +28,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -36,7 +37,7 @@ namespace {
 inline size_t err(u32 code) { return (size_t)0 - (size_t)code; }
 
 // ------------------------------------------------------------------ pinned host memory, pooled
-struct Arena { u8* p = nullptr; size_t cap = 0; };
+struct Arena { u8* p = nullptr; size_t cap = 0; bool pinned = true; };
 
 class PinnedPool {
     std::mutex mu_;
@@ -73,11 +74,16 @@ public:
             trim(0);
             a.p = (u8*)kzg_host_alloc(want);
         }
+        if (!a.p) {                                        // no pinned memory left: pageable memory still works (slower copies)
+            a.p = (u8*)malloc(want);
+            a.pinned = false;
+        }
         a.cap = a.p ? want : 0;
         return a;
     }
     void release(Arena& a) {
         if (!a.p) return;
+        if (!a.pinned) { free(a.p); a = Arena(); return; }
         {
             std::lock_guard<std::mutex> lock(mu_);
             if (kept_ + a.cap <= kKeepBytes) { free_.push_back(a); kept_ += a.cap; a = Arena(); return; }
