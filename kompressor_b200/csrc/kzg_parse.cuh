@@ -47,8 +47,29 @@ KZG_HD u32 kzg_parse_frame_header(const u8* src, u64 size, KzgFrameHeader& h) {
 
 // ---------------------------------------------------------------------------------------------
 // FSE normalised counts (Appendix A.5).  Returns bytes consumed, or 0 on error.
+// Forward bit reader over a 64-bit window that is refilled a few bytes at a time (the description is read in
+// fields of at most 10 bits: one load per field would be five times as many loads).
+struct KzgFwdWin {
+    const u8* p; u32 size;
+    u64 win; u32 base;                      // win = bytes [base, base + 8) of p, bytes past `size` read as zero
+    KZG_HD void fill(u32 byte) {
+        base = byte;
+        win = 0;
+        for (u32 k = 0; k < 8; k++)
+            if (byte + k < size) win |= (u64)p[byte + k] << (8 * k);
+    }
+    KZG_HD u32 bits(u32 bitpos, u32 n) {    // n <= 24
+        const u32 byte = bitpos >> 3;
+        if (byte < base || byte + 4 > base + 8) fill(byte);
+        return (u32)(win >> (bitpos - 8 * base)) & ((1u << n) - 1u);
+    }
+};
+
 KZG_HD u32 kzg_read_ncount(const u8* src, u32 size, u32 max_sym, u32 max_log, i16* norm, u32& nsym, u32& log) {
     if (size < 1) return 0;
+    KzgFwdWin r;
+    r.p = src; r.size = size;
+    r.fill(0);
     u32 bitpos = 4;
     log = 5 + (src[0] & 15);
     if (log > max_log) return 0;
@@ -57,7 +78,7 @@ KZG_HD u32 kzg_read_ncount(const u8* src, u32 size, u32 max_sym, u32 max_log, i1
     while (remaining > 0) {
         if (sym > max_sym) return 0;
         const u32 bits = (u32)kzg_highbit((u32)remaining + 1) + 1;
-        i32 v = (i32)kzg_fwd_bits(src, size, bitpos, bits);
+        i32 v = (i32)r.bits(bitpos, bits);
         bitpos += bits;
         const i32 lower = (1 << (bits - 1)) - 1;
         const i32 thr = (1 << bits) - 1 - (remaining + 1);
@@ -69,7 +90,7 @@ KZG_HD u32 kzg_read_ncount(const u8* src, u32 size, u32 max_sym, u32 max_log, i1
         norm[sym++] = (i16)prob;
         if (prob == 0) {
             for (;;) {
-                const u32 rep = kzg_fwd_bits(src, size, bitpos, 2);
+                const u32 rep = r.bits(bitpos, 2);
                 bitpos += 2;
                 for (u32 i = 0; i < rep; i++) {
                     if (sym > max_sym) return 0;
@@ -120,7 +141,11 @@ KZG_HD u32 kzg_read_huf_weights(const u8* src, u32 size, u8* w, u32& nsym_out, u
         n = hb - 127;
         used = 1 + (n + 1) / 2;
         if (used > size) return 0;
-        for (u32 i = 0; i < n; i++) w[i] = (i & 1) ? (src[1 + i / 2] & 15) : (src[1 + i / 2] >> 4);
+        for (u32 k = 0; 2 * k < n; k++) {               // two weights per byte, high nibble first
+            const u32 b = src[1 + k];
+            w[2 * k] = (u8)(b >> 4);
+            if (2 * k + 1 < n) w[2 * k + 1] = (u8)(b & 15);
+        }
     } else {
         used = 1 + hb;
         if (used > size) return 0;
