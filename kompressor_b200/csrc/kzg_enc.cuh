@@ -587,45 +587,66 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             if (rep_hit) cand = (i32)(p - rep);
             const bool hit = rep_hit || (ok && cand >= 0 && lds32u(base + (u32)cand) == v);
             const u32 m = __ballot_sync(0xFFFFFFFFu, hit);
-            // positions up to the match start enter the table; the ones behind it are probed again by a later step
-            // and must still find their older candidates then
-            const u32 l = m ? __ffs(m) - 1 : 31u;
-            if (ok && lane <= l) table[h] = (u16)p;
+            if (m == 0) {                                        // nothing here: all 32 positions enter the table
+                if (ok) table[h] = (u16)p;
+                __syncwarp();
+                pos += 32;
+                continue;
+            }
+            // Every hit of this step that starts at or behind the end of the previous match becomes a sequence (short
+            // matches are the rule: probing again for each of them would cost more than it finds).  Positions outside
+            // the matches enter the table; the ones behind the last match are probed again by the next step and must
+            // still find their older candidates then.
+            u32 avail = m, ins = 0, from = 0;                    // hits still usable; lanes to insert; first lane not yet covered
+            bool full = false;
+            while (avail) {
+                const u32 l = __ffs(avail) - 1;
+                ins |= (l == 31 ? 0xFFFFFFFFu : ((2u << l) - 1u)) & ~((1u << from) - 1u);      // lanes from .. l
+                u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
+                u32 len = 4;
+                {   // backward extension into the pending literals (at most 32 bytes)
+                    const bool same = ms > anchor + lane && mc > lane && lds8(base + ms - 1 - lane) == lds8(base + mc - 1 - lane);
+                    const u32 stop = __ballot_sync(0xFFFFFFFFu, !same);
+                    const u32 back = stop ? __ffs(stop) - 1 : 32u;
+                    ms -= back; mc -= back; len += back;
+                }
+                // forward extension inside the part, 128 bytes per step
+                for (;;) {
+                    const u32 k = len + 4 * lane;
+                    const i32 rem = (i32)q1 - (i32)(ms + k);         // bytes of this lane's word that belong to the part
+                    u32 diff = 1u;
+                    if (rem > 0) {
+                        diff = lds32u(base + ms + k) ^ lds32u(base + mc + k);
+                        if (rem < 4) diff = (diff & ((1u << (8 * rem)) - 1u)) | (1u << (8 * rem));
+                    }
+                    const u32 mm = __ballot_sync(0xFFFFFFFFu, diff != 0);
+                    if (mm) {
+                        const u32 fl = __ffs(mm) - 1;
+                        const u32 d = __shfl_sync(0xFFFFFFFFu, diff, fl);
+                        len += 4 * fl + (((u32)__ffs(d) - 1) >> 3);
+                        break;
+                    }
+                    len += 128;
+                }
+                const u32 ll = ms - anchor;
+                if (lane == 0) seqq[nseq] = (u64)ll | ((u64)len << 18) | ((u64)(ms - mc) << 36);
+                nseq++;
+                nlit += ll;
+                anchor = ms + len;
+                rep = ms - mc;
+                if (nseq == qcap) { full = true; break; }
+                const u32 end_rel = anchor - pos;                // first position behind the match, relative to this step
+                if (end_rel >= 32) break;
+                from = end_rel;
+                // the distance of this match is the repeat distance for what follows: probe it for the positions left
+                const bool again = ok && lane >= end_rel && p >= rep && lds32u(base + p - rep) == v;
+                if (again) cand = (i32)(p - rep);
+                avail = (avail | __ballot_sync(0xFFFFFFFFu, again)) & ~((1u << end_rel) - 1u);
+            }
+            if (ok && ((ins >> lane) & 1u)) table[h] = (u16)p;
             __syncwarp();
-            if (m == 0) { pos += 32; continue; }
-            u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
-            u32 len = 4;
-            {   // backward extension into the pending literals (at most 32 bytes)
-                const bool same = ms > anchor + lane && mc > lane && lds8(base + ms - 1 - lane) == lds8(base + mc - 1 - lane);
-                const u32 stop = __ballot_sync(0xFFFFFFFFu, !same);
-                const u32 back = stop ? __ffs(stop) - 1 : 32u;
-                ms -= back; mc -= back; len += back;
-            }
-            // forward extension inside the part, 128 bytes per step
-            for (;;) {
-                const u32 k = len + 4 * lane;
-                const i32 rem = (i32)q1 - (i32)(ms + k);             // bytes of this lane's word that belong to the part
-                u32 diff = 1u;
-                if (rem > 0) {
-                    diff = lds32u(base + ms + k) ^ lds32u(base + mc + k);
-                    if (rem < 4) diff = (diff & ((1u << (8 * rem)) - 1u)) | (1u << (8 * rem));
-                }
-                const u32 mm = __ballot_sync(0xFFFFFFFFu, diff != 0);
-                if (mm) {
-                    const u32 fl = __ffs(mm) - 1;
-                    const u32 d = __shfl_sync(0xFFFFFFFFu, diff, fl);
-                    len += 4 * fl + (((u32)__ffs(d) - 1) >> 3);
-                    break;
-                }
-                len += 128;
-            }
-            const u32 ll = ms - anchor;
-            if (lane == 0) seqq[nseq] = (u64)ll | ((u64)len << 18) | ((u64)(ms - mc) << 36);
-            nseq++;
-            nlit += ll;
-            anchor = pos = ms + len;
-            rep = ms - mc;
-            if (nseq == qcap) break;
+            pos = anchor;
+            if (full) break;
         }
         const u32 tail = q1 - anchor;
         if (lane == 0) { misc[warp] = nseq; misc[8 + warp] = nlit + tail; misc[16 + warp] = tail; }
