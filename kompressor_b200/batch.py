@@ -190,8 +190,9 @@ class BatchEncoder:
     def bound(self, n: int) -> int:
         return int(self._L.kzg_compress_bound(n))
 
-    def compress_chunks(self, data: np.ndarray, offsets: np.ndarray, sizes: np.ndarray, checksum: bool = False):
-        """Host memory in, host memory out -> (buffer, frame offsets, frame sizes, status)."""
+    def compress_chunks(self, data: np.ndarray, offsets: np.ndarray, sizes: np.ndarray, checksum: bool = False, level: int = 3):
+        """Host memory in, host memory out -> (buffer, frame offsets, frame sizes, status).
+        level < 3: greedy parse; level >= 3: one step of lazy matching (about 2 % smaller, match stage 25 % slower)."""
         n = int(len(offsets))
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
@@ -205,12 +206,12 @@ class BatchEncoder:
         out_size = np.zeros(n, np.uint64)
         rc = self._L.kzg_compress_batch_host(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data,
                                              sizes.ctypes.data, out.ctypes.data, doff.ctypes.data, caps.ctypes.data, n,
-                                             1 if checksum else 0, status.ctypes.data, out_size.ctypes.data)
+                                             (1 if checksum else 0) | (2 if level >= 3 else 0), status.ctypes.data, out_size.ctypes.data)
         if rc < 0:
             raise KzgError(f"kzg_compress_batch_host failed: {rc}")
         return out, doff, out_size, status
 
-    def compress(self, data, chunk_size: int = 65536, checksum: bool = False) -> bytes:
+    def compress(self, data, chunk_size: int = 65536, checksum: bool = False, level: int = 3) -> bytes:
         """Cuts `data` into chunks of chunk_size and returns the concatenated frames (a valid zstd stream: any
         decoder yields `data` again)."""
         a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
@@ -219,7 +220,7 @@ class BatchEncoder:
         n = max(1, (a.size + chunk_size - 1) // chunk_size)
         offsets = np.arange(n, dtype=np.uint64) * np.uint64(chunk_size)
         sizes = np.minimum(np.uint64(chunk_size), np.uint64(a.size) - offsets).astype(np.uint64) if a.size else np.zeros(1, np.uint64)
-        out, doff, osz, status = self.compress_chunks(a, offsets, sizes, checksum)
+        out, doff, osz, status = self.compress_chunks(a, offsets, sizes, checksum, level)
         if status.any():
             raise KzgError(f"compress failed: status {status[status != 0][0]}")
         return b"".join(out[int(o):int(o) + int(s)].tobytes() for o, s in zip(doff, osz))

@@ -28,6 +28,7 @@
 #define KZG_ENC_HASH_LOG 11          // per-warp table: 2048 entries of 16 bits
 #define KZG_ENC_WARPS 8              // = parts per chunk (each warp parses one)
 #define KZG_ENC_FLAG_CHECKSUM 1u
+#define KZG_ENC_FLAG_LAZY 2u          // one step of lazy matching (better ratio, slower match stage)
 #define KZG_ENC_ST_RAW 1u            // chunk state after encode: emit a raw block
 #define KZG_ENC_ST_COMPRESSED 2u
 #define KZG_ENC_ST_ERROR 3u
@@ -528,6 +529,7 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
     // misc: [0,8) sequences, [8,16) literal bytes, [16,24) tail literals of the parts, [24] ticket
     u32* const misc = reinterpret_cast<u32*>(sm + chunk_cap + 32 + KZG_ENC_WARPS * KZG_ENC_TABLE_BYTES);
     const u32 s_chunk = smem_addr(sm);
+    const bool lazy = (B.flags & KZG_ENC_FLAG_LAZY) != 0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) misc[24] = atomicAdd(&B.tickets[0], 1u);
@@ -599,34 +601,42 @@ __global__ void __launch_bounds__(KZG_ENC_WARPS * 32) kzg_enc_match_kernel(KzgEn
             // still find their older candidates then.
             u32 avail = m, ins = 0, from = 0;                    // hits still usable; lanes to insert; first lane not yet covered
             bool full = false;
-            while (avail) {
-                const u32 l = __ffs(avail) - 1;
-                ins |= (l == 31 ? 0xFFFFFFFFu : ((2u << l) - 1u)) & ~((1u << from) - 1u);      // lanes from .. l
-                u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
-                u32 len = 4;
-                {   // backward extension into the pending literals (at most 32 bytes)
-                    const bool same = ms > anchor + lane && mc > lane && lds8(base + ms - 1 - lane) == lds8(base + mc - 1 - lane);
-                    const u32 stop = __ballot_sync(0xFFFFFFFFu, !same);
-                    const u32 back = stop ? __ffs(stop) - 1 : 32u;
-                    ms -= back; mc -= back; len += back;
-                }
-                // forward extension inside the part, 128 bytes per step
-                for (;;) {
+            // length of the match between positions a and b (b < a) beyond their first `have` bytes, inside the part
+            auto extend = [&](u32 a, u32 b, u32 have) {
+                u32 len = have;
+                for (;;) {                                       // 128 bytes per step
                     const u32 k = len + 4 * lane;
-                    const i32 rem = (i32)q1 - (i32)(ms + k);         // bytes of this lane's word that belong to the part
+                    const i32 rem = (i32)q1 - (i32)(a + k);      // bytes of this lane's word that belong to the part
                     u32 diff = 1u;
                     if (rem > 0) {
-                        diff = lds32u(base + ms + k) ^ lds32u(base + mc + k);
+                        diff = lds32u(base + a + k) ^ lds32u(base + b + k);
                         if (rem < 4) diff = (diff & ((1u << (8 * rem)) - 1u)) | (1u << (8 * rem));
                     }
                     const u32 mm = __ballot_sync(0xFFFFFFFFu, diff != 0);
                     if (mm) {
                         const u32 fl = __ffs(mm) - 1;
                         const u32 d = __shfl_sync(0xFFFFFFFFu, diff, fl);
-                        len += 4 * fl + (((u32)__ffs(d) - 1) >> 3);
-                        break;
+                        return len + 4 * fl + (((u32)__ffs(d) - 1) >> 3);
                     }
                     len += 128;
+                }
+            };
+            while (avail) {
+                u32 l = __ffs(avail) - 1;
+                u32 ms = pos + l, mc = (u32)__shfl_sync(0xFFFFFFFFu, cand, l);
+                u32 len = extend(ms, mc, 4);
+                // one step of lazy matching: a hit at the next position that is longer by more than the literal it costs
+                if (lazy && l < 31 && ((avail >> (l + 1)) & 1u)) {
+                    const u32 mc2 = (u32)__shfl_sync(0xFFFFFFFFu, cand, l + 1);
+                    const u32 len2 = extend(ms + 1, mc2, 4);
+                    if (len2 > len + 1) { l++; ms++; mc = mc2; len = len2; }
+                }
+                ins |= (l == 31 ? 0xFFFFFFFFu : ((2u << l) - 1u)) & ~((1u << from) - 1u);      // lanes from .. l
+                {   // backward extension into the pending literals (at most 32 bytes)
+                    const bool same = ms > anchor + lane && mc > lane && lds8(base + ms - 1 - lane) == lds8(base + mc - 1 - lane);
+                    const u32 stop = __ballot_sync(0xFFFFFFFFu, !same);
+                    const u32 back = stop ? __ffs(stop) - 1 : 32u;
+                    ms -= back; mc -= back; len += back;
                 }
                 const u32 ll = ms - anchor;
                 if (lane == 0) seqq[nseq] = (u64)ll | ((u64)len << 18) | ((u64)(ms - mc) << 36);

@@ -417,6 +417,7 @@ struct kzg_CCtx {
     Arena out;                       // frames not yet handed to the caller: out.p[out_pos, out_size)
     size_t out_size = 0, out_pos = 0;
     bool checksum = false;
+    bool lazy = true;                // compression level >= 3 (the reference's default)
     bool wrote_frame = false;        // since the last completed e_end
     std::vector<uint64_t> off, size, doff, cap, osize;
     std::vector<uint32_t> status;
@@ -439,9 +440,10 @@ extern "C" size_t kzg_freeCCtx(kzg_CCtx* c) {
 extern "C" size_t kzg_CCtx_setParameter(kzg_CCtx* c, int param, int value) {
     if (!c) return err(KZG_E_GENERIC);
     if (param == 201) { c->checksum = value != 0; return 0; }               // ZSTD_c_checksumFlag
-    // compression level, window / hash / chain / search logs, minMatch, targetLength, strategy, content-size and
-    // dictionary-ID flags: accepted; the frame writer has one fixed parse and always writes the content size
-    if ((param >= 100 && param <= 107) || param == 200 || param == 202) return 0;
+    if (param == 100) { c->lazy = value >= 3; return 0; }                   // ZSTD_c_compressionLevel: greedy below 3, lazy from 3
+    // window / hash / chain / search logs, minMatch, targetLength, strategy, content-size and dictionary-ID flags:
+    // accepted without effect; the frame writer always writes the content size
+    if ((param >= 101 && param <= 107) || param == 200 || param == 202) return 0;
     return err(40 /* parameter_unsupported */);
 }
 
@@ -480,7 +482,7 @@ static size_t compress_buffered(kzg_CCtx* c, size_t nbytes) {
     {
         std::lock_guard<std::mutex> lock(g_enc_mu);
         rc = kzg_compress_batch_host(g_enc, c->in.data(), c->off.data(), c->size.data(), c->out.p + pending, c->doff.data(),
-                                     c->cap.data(), n, c->checksum ? KZG_COMPRESS_CHECKSUM : 0, c->status.data(), c->osize.data());
+                                     c->cap.data(), n, (c->checksum ? KZG_COMPRESS_CHECKSUM : 0) | (c->lazy ? KZG_COMPRESS_LAZY : 0), c->status.data(), c->osize.data());
     }
     if (rc < 0) return err((u32)(-rc));
     size_t w = pending;

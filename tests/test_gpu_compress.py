@@ -67,3 +67,16 @@ def test_output_is_deterministic(enc):
     import corpus
     data = bytes(corpus.generate("logs", 9, 1 << 20))
     assert enc.compress(data) == enc.compress(data)
+
+
+def test_level_selects_the_parse(enc, libzstd):
+    """compressionLevel below 3: greedy parse; from 3 (Kompressor's default): one step of lazy matching, never larger
+    on text.  Both decode with libzstd."""
+    import corpus
+    data = bytes(corpus.generate("logs", 55, 2 << 20))
+    greedy = enc.compress(data, level=1)
+    lazy = enc.compress(data, level=3)
+    for comp in (greedy, lazy):
+        out, err = libzstd.decompress_oneshot(comp, len(data) + 64)
+        assert err == 0 and out == data
+    assert len(lazy) < len(greedy)
