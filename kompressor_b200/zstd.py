@@ -70,7 +70,7 @@ class ZstdDecompressorImpl(SliceTransform):
 
 class ZstdCompressorImpl(SliceTransform):
     """ZstdCompressor.jvm.kt:10-42 on top of the kzg frame writer (compress side of the shim).  The stream is written
-    as independent 64 KiB frames; `compressionLevel` is accepted and has no effect (one fixed parse)."""
+    as independent 64 KiB frames; `compressionLevel` below 3 selects the greedy parse, from 3 one step of lazy matching."""
 
     def __init__(self, compressionLevel: int = 3, dictionary: bytes | None = None):
         self._L = lib()
