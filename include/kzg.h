@@ -57,6 +57,15 @@ void kzg_ctx_destroy(kzg_ctx* ctx);
 size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, uint64_t* size, uint64_t* content,
                        size_t max_frames, size_t* consumed);
 
+/* Seek table of the zstd seekable format: a skippable frame {0x184D2A5E, size, n x {compressed size, content size},
+ * n, descriptor, 0x8F92EAB1} appended to a stream of frames ("independent frames with
+ * a seekable index").  kzg_write_seek_table writes it for n frames (returns its size, kzg_seek_table_bound(n), or an
+ * error code).  kzg_scan_frames uses a trailing table when it describes the buffer exactly (one pass over 8 bytes per
+ * frame instead of a walk over every block header) and falls back to the walk otherwise; the table's own skippable
+ * frame is reported as the last entry, like any skippable frame. */
+size_t kzg_seek_table_bound(size_t n_frames);
+size_t kzg_write_seek_table(void* dst, size_t cap, const uint64_t* comp_size, const uint64_t* content_size, size_t n_frames);
+
 /* Decodes n_frames independent frames whose bytes are already in device memory.
  *   d_src + d_src_off[i], d_src_size[i]   exactly one zstd (or skippable) frame each
  *   d_dst + d_dst_off[i], d_dst_cap[i]    where its output goes and how much room there is

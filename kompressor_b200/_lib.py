@@ -39,6 +39,7 @@ EXPORTS = [
     "kzg_enc_create", "kzg_enc_destroy", "kzg_compress_bound", "kzg_compress_batch_device", "kzg_enc_finish",
     "kzg_compress_batch_host", "kzg_enc_set_profiling", "kzg_enc_last_stage_ms",
     "kzg_createCCtx", "kzg_freeCCtx", "kzg_CCtx_setParameter", "kzg_CCtx_loadDictionary", "kzg_compressStream2",
+    "kzg_seek_table_bound", "kzg_write_seek_table",
 ]
 
 _lib = None
@@ -101,6 +102,10 @@ def lib() -> ctypes.CDLL:
     L.kzg_enc_set_profiling.restype = c_int
     L.kzg_enc_last_stage_ms.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
     L.kzg_enc_last_stage_ms.restype = c_int
+    L.kzg_seek_table_bound.argtypes = [c_size_t]
+    L.kzg_seek_table_bound.restype = c_size_t
+    L.kzg_write_seek_table.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t]
+    L.kzg_write_seek_table.restype = c_size_t
     L.kzg_createCCtx.restype = c_void_p
     L.kzg_freeCCtx.argtypes = [c_void_p]
     L.kzg_freeCCtx.restype = c_size_t

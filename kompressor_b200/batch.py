@@ -211,7 +211,7 @@ class BatchEncoder:
             raise KzgError(f"kzg_compress_batch_host failed: {rc}")
         return out, doff, out_size, status
 
-    def compress(self, data, chunk_size: int = 65536, checksum: bool = False, level: int = 3) -> bytes:
+    def compress(self, data, chunk_size: int = 65536, checksum: bool = False, level: int = 3, seek_table: bool = False) -> bytes:
         """Cuts `data` into chunks of chunk_size and returns the concatenated frames (a valid zstd stream: any
         decoder yields `data` again)."""
         a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
@@ -223,7 +223,17 @@ class BatchEncoder:
         out, doff, osz, status = self.compress_chunks(a, offsets, sizes, checksum, level)
         if status.any():
             raise KzgError(f"compress failed: status {status[status != 0][0]}")
-        return b"".join(out[int(o):int(o) + int(s)].tobytes() for o, s in zip(doff, osz))
+        frames = b"".join(out[int(o):int(o) + int(s)].tobytes() for o, s in zip(doff, osz))
+        if not seek_table:
+            return frames
+        # the seekable format's index: a skippable frame that lists every frame's compressed and content size
+        cap = int(self._L.kzg_seek_table_bound(n))
+        tab = np.zeros(cap, np.uint8)
+        osz64 = np.ascontiguousarray(osz, dtype=np.uint64)
+        wrote = self._L.kzg_write_seek_table(tab.ctypes.data, cap, osz64.ctypes.data, sizes.ctypes.data, n)
+        if self._L.kzg_isError(wrote):
+            raise KzgError("kzg_write_seek_table failed")
+        return frames + tab[:wrote].tobytes()
 
     def set_profiling(self, enable: bool = True) -> None:
         self._L.kzg_enc_set_profiling(self._h, int(enable))

@@ -230,11 +230,72 @@ extern "C" void* kzg_host_alloc(size_t bytes) {
 extern "C" void kzg_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------------
+// Seek table of the zstd seekable format (contrib/seekable_format): a skippable frame at the end of the stream,
+//   0x184D2A5E | frame size | n entries {compressed size, decompressed size [, checksum]} | n | descriptor | 0x8F92EAB1
+// The batch frame writer can append one (kzg_write_seek_table); with it the frame table of a stream comes from one
+// pass over 8 bytes per frame instead of a walk over every block header.
+#define KZG_SEEK_SKIP_MAGIC 0x184D2A5Eu
+#define KZG_SEEK_MAGIC 0x8F92EAB1u
+
+extern "C" size_t kzg_seek_table_bound(size_t n_frames) { return 8 + n_frames * 8 + 9; }
+
+extern "C" size_t kzg_write_seek_table(void* dst, size_t cap, const uint64_t* comp_size, const uint64_t* content_size, size_t n) {
+    const size_t need = kzg_seek_table_bound(n);
+    if (!dst || cap < need || n > 0x7FFFFFFu) return (size_t)0 - (size_t)KZG_E_DSTSIZE_TOO_SMALL;
+    u8* p = (u8*)dst;
+    auto w32 = [&](u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); p += 4; };
+    w32(KZG_SEEK_SKIP_MAGIC);
+    w32((u32)(need - 8));
+    for (size_t i = 0; i < n; i++) {
+        if (comp_size[i] > 0xFFFFFFFFull || content_size[i] > 0xFFFFFFFFull) return (size_t)0 - (size_t)KZG_E_GENERIC;
+        w32((u32)comp_size[i]);
+        w32((u32)content_size[i]);
+    }
+    w32((u32)n);
+    *p++ = 0;                                   // descriptor: no per-frame checksums
+    w32(KZG_SEEK_MAGIC);
+    return need;
+}
+
+// Frame table from a trailing seek table. Returns the number of entries written (the table's own skippable frame is
+// the last one), or 0 if there is no table, it does not describe this buffer exactly, or it does not fit max_frames.
+static size_t scan_by_seek_table(const u8* p, size_t len, uint64_t* off, uint64_t* size, uint64_t* content, size_t max_frames) {
+    if (len < 17 || kzg_rd32(p + len - 4) != KZG_SEEK_MAGIC) return 0;
+    const u32 desc = p[len - 5], n = kzg_rd32(p + len - 9);
+    if (desc & 0x7C) return 0;
+    const size_t entry = (desc & 0x80) ? 12 : 8;
+    const u64 table = (u64)n * entry + 9;
+    if (table + 8 > len || (u64)n + 1 > max_frames) return 0;
+    const size_t tpos = len - (size_t)table - 8;
+    if (kzg_rd32(p + tpos) != KZG_SEEK_SKIP_MAGIC || kzg_rd32(p + tpos + 4) != table) return 0;
+    u64 pos = 0;
+    for (u32 i = 0; i < n; i++) {
+        const u8* e = p + tpos + 8 + (size_t)i * entry;
+        const u64 cs = kzg_rd32(e), ds = kzg_rd32(e + 4);
+        if (cs < 4 || pos + cs > tpos) return 0;
+        const u32 magic = kzg_rd32(p + pos);
+        if (magic != KZG_MAGIC && (magic & 0xFFFFFFF0u) != KZG_SKIP_MAGIC) return 0;
+        if (off) off[i] = pos;
+        if (size) size[i] = cs;
+        if (content) content[i] = magic == KZG_MAGIC ? ds : 0;
+        pos += cs;
+    }
+    if (pos != tpos) return 0;                  // the entries must cover everything in front of the table
+    if (off) off[n] = tpos;
+    if (size) size[n] = table + 8;
+    if (content) content[n] = 0;
+    return (size_t)n + 1;
+}
+
 extern "C" size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, uint64_t* size, uint64_t* content,
                                   size_t max_frames, size_t* consumed) {
     const u8* p = (const u8*)buf;
     size_t pos = 0, n = 0;
     if (consumed) *consumed = 0;
+    if (const size_t k = scan_by_seek_table(p, len, off, size, content, max_frames)) {
+        if (consumed) *consumed = len;
+        return k;
+    }
     while (pos < len && n < max_frames) {
         const u8* f = p + pos;
         const size_t rem = len - pos;

@@ -98,3 +98,41 @@ def test_jni_shim_typechecks_and_names_the_reference_symbols():
     assert defined == {"JNI_OnLoad", "JNI_OnUnload"} | {"Java_com_ensody_kompressor_zstd_ZstdWrapper_" + n for n in (
         "createDecompressor", "freeDecompressor", "loadDecompressorDictionary", "decompressStream", "getErrorName",
         "createCompressor", "freeCompressor", "setParameter", "loadCompressorDictionary", "compressStream")}
+
+
+def test_seek_table_roundtrip(kzg_lib, libzstd):
+    """zstd seekable-format index (host code, no GPU): written by kzg_write_seek_table, used by kzg_scan_frames when it
+    describes the buffer exactly, ignored (plain walk) when it does not; libzstd skips it like any skippable frame."""
+    import ctypes
+    import corpus
+    from kompressor_b200._lib import lib
+    from kompressor_b200.batch import scan_frames
+    L = lib()
+    raws = [bytes(corpus.generate("logs", 900 + i, 3000 + 777 * i)) for i in range(9)]
+    frames = [libzstd.compress(r, 3, checksum=bool(i & 1)) for i, r in enumerate(raws)]
+    body = b"".join(frames)
+    n = len(frames)
+    comp = np.array([len(f) for f in frames], np.uint64)
+    cont = np.array([len(r) for r in raws], np.uint64)
+    cap = int(L.kzg_seek_table_bound(n))
+    assert cap == 8 + 8 * n + 9
+    tab = np.zeros(cap, np.uint8)
+    assert L.kzg_write_seek_table(tab.ctypes.data, cap, comp.ctypes.data, cont.ctypes.data, n) == cap
+    assert L.kzg_isError(L.kzg_write_seek_table(tab.ctypes.data, cap - 1, comp.ctypes.data, cont.ctypes.data, n))
+    table = tab.tobytes()
+    assert table[:4] == bytes.fromhex("5e2a4d18") and table[-4:] == bytes.fromhex("b1ea928f")
+    blob = body + table
+    off, size, content, consumed = scan_frames(blob)
+    assert consumed == len(blob) and len(off) == n + 1
+    assert list(size[:n]) == list(comp) and list(content[:n]) == list(cont)
+    assert int(off[n]) == len(body) and int(size[n]) == cap and int(content[n]) == 0
+    # the same table in front of one more frame does not describe the buffer: plain walk, same frames
+    off2, size2, content2, consumed2 = scan_frames(blob + frames[0])
+    assert len(off2) == n + 2 and list(size2[:n]) == list(comp) and consumed2 == len(blob) + len(frames[0])
+    # an entry that does not match: plain walk again
+    bad = bytearray(blob)
+    bad[len(body) + 8] ^= 1
+    off3, size3, _, _ = scan_frames(bytes(bad))
+    assert list(size3[:n]) == list(comp)
+    out, err = libzstd.decompress_oneshot(blob, sum(len(r) for r in raws) + 64)
+    assert err == 0 and out == b"".join(raws)

@@ -80,3 +80,19 @@ def test_level_selects_the_parse(enc, libzstd):
         out, err = libzstd.decompress_oneshot(comp, len(data) + 64)
         assert err == 0 and out == data
     assert len(lazy) < len(greedy)
+
+
+def test_seek_table_stream(enc, libzstd):
+    """The frame writer's stream with a seekable index at its end decodes everywhere, and the index gives the frame
+    table without a walk."""
+    import corpus
+    from kompressor_b200 import core, zstd
+    from kompressor_b200.batch import scan_frames
+    data = bytes(corpus.generate("json", 91, 1000003))
+    comp = enc.compress(data, seek_table=True)
+    assert comp[-4:] == bytes.fromhex("b1ea928f")
+    off, size, content, consumed = scan_frames(comp)
+    assert consumed == len(comp) and len(off) == 16 + 1 and int(content[:16].sum()) == len(data)
+    out, err = libzstd.decompress_oneshot(comp, len(data) + 64)
+    assert err == 0 and out == data
+    assert core.transform(zstd.ZstdDecompressor(), comp) == data
