@@ -1,5 +1,5 @@
 """Timing of BASELINE.json's other configs on one GPU (development):
-   python scripts/gpu_configs.py [scale]   (scale 1.0 = 1 GiB per config, except level 19)"""
+   python scripts/gpu_configs.py [scale] [kind ...]   (scale 1.0 = 1 GiB per config, except level 19; kinds: all)"""
 import sys, time
 sys.path.insert(0, ".")
 import numpy as np
@@ -8,12 +8,15 @@ import corpus
 from kompressor_b200.batch import BatchDecoder
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.25
+only = set(sys.argv[2:])
 dec = BatchDecoder()
 dec.set_profiling(True)
 cases = [("logs", 65536, 3, False, False, int(16384 * scale)), ("json", 65536, 3, True, False, int(16384 * scale)),
          ("literal", 65536, 1, False, False, int(16384 * scale)), ("random", 131075, 3, False, False, 256),
          ("mixed", 4 << 20, 19, False, True, 16)]
 for kind, fs, lvl, cs, streamed, n in cases:
+    if only and kind not in only:
+        continue
     t = time.time()
     c = corpus.build(kind, n, fs, lvl, cs, streamed=streamed)
     caps = np.full(n, fs, np.uint64)
