@@ -136,3 +136,21 @@ def test_seek_table_roundtrip(kzg_lib, libzstd):
     assert list(size3[:n]) == list(comp)
     out, err = libzstd.decompress_oneshot(blob, sum(len(r) for r in raws) + 64)
     assert err == 0 and out == b"".join(raws)
+
+
+def test_seek_table_with_checksum_entries(kzg_lib, libzstd):
+    """A seek table written by another tool may carry a checksum per entry (descriptor bit 7: 12-byte entries)."""
+    import struct
+    from kompressor_b200.batch import scan_frames
+    raws = [bytes([65 + i]) * (1000 + i) for i in range(5)]
+    frames = [libzstd.compress(r, 3) for r in raws]
+    body = b"".join(frames)
+    entries = b"".join(struct.pack("<III", len(f), len(r), 0xDEADBEEF) for f, r in zip(frames, raws))
+    table = struct.pack("<II", 0x184D2A5E, len(entries) + 9) + entries + struct.pack("<IBI", len(frames), 0x80, 0x8F92EAB1)
+    off, size, content, consumed = scan_frames(body + table)
+    assert consumed == len(body) + len(table) and len(off) == 6
+    assert [int(x) for x in content[:5]] == [len(r) for r in raws] and int(size[5]) == len(table)
+    # reserved descriptor bits set: not a table this reader accepts -> plain walk, same result
+    bad = body + table[:-5] + bytes([0x84]) + table[-4:]
+    off2, size2, _, _ = scan_frames(bad)
+    assert len(off2) == 6 and [int(x) for x in size2[:5]] == [len(f) for f in frames]
