@@ -398,6 +398,36 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                     const u32 l_ll = __shfl_sync(0xFFFFFFFFu, ll, stop), l_ml = __shfl_sync(0xFFFFFFFFu, ml, stop);
                     const u32 l_ple = __shfl_sync(0xFFFFFFFFu, p_lit_end, stop), l_poe = __shfl_sync(0xFFFFFFFFu, p_out_end, stop);
                     const u32 l_off = __shfl_sync(0xFFFFFFFFu, off, stop);
+                    // (FULL variant) A medium-long match with short literals stays inside the window: the lane copies its
+                    // literals, the warp copies the match 32 bytes per step (a source at least 32 bytes behind, or disjoint).
+                    {
+                        const i32 sp0 = (i32)(l_poe + l_ll) - (i32)l_off;
+                        if (FULL && l_ll <= KZG_EX_LONG && (this_staged || lfill) && l_ml <= 1024u && (l_off >= 32u || l_off >= l_ml) && w.boff + sp0 >= 0) {
+                            const i32 end = (i32)(l_poe + l_ll + l_ml);
+                            if ((u32)(end - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); }
+                            const bool in_win = sp0 >= w.Tv, in_glob = sp0 + (i32)l_ml <= w.F;
+                            if ((u32)(end - w.T0) <= KZG_EX_TILE && (in_win || in_glob)) {
+                                lane_copy(w.tile + (u32)((i32)l_poe - w.T0), lane == stop ? ll : 0u, lsrc, lfill, rle);
+                                __syncwarp();
+                                const u32 da = w.tile + (u32)((i32)(l_poe + l_ll) - w.T0);
+                                if (in_win) {
+                                    const u32 sa = w.tile + (u32)(sp0 - w.T0);
+                                    for (u32 k0 = 0; k0 < l_ml; k0 += 32) {
+                                        const u32 k = k0 + lane;
+                                        const u32 v = k < l_ml ? lds8(sa + k) : 0u;
+                                        if (k < l_ml) sts8(da + k, v);
+                                        __syncwarp();
+                                    }
+                                } else {
+                                    for (u32 k = lane; k < l_ml; k += 32) sts8(da + k, ldg8_hist(out + sp0 + (i32)k));
+                                    __syncwarp();
+                                }
+                                cur = end;
+                                todo &= ~(1u << stop);
+                                continue;
+                            }
+                        }
+                    }
                     if (!FULL && l_off < l_ml && l_ml >= 1024u) { defer = true; break; }      // a long run: left to the FULL variant
                     flush(w, cur, true, lane);
                     __syncwarp();
@@ -498,6 +528,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
 // FULL = false: the hot variant.  It has no code for long overlapping matches (runs); a frame that contains one is
 // put on the deferred list and executed again, from its first block, by the FULL = true variant, which is launched
 // right after over that list only.  Keeping the rare path out of the hot kernel is worth ~5 % of its speed.
+#define KZG_EX_BIG_FRAME_BLOCKS 8u
 template <bool FULL>
 __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch B) {
     using namespace kzg_ex;
@@ -516,7 +547,9 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch
         u8* const fdst = B.dst + B.dst_off[f];
         const u32 nblk = fr->n_blocks, first = fr->first_block;
         bool failed = false;
-        bool deferred = false;
+        // frames of many blocks (large windows, long matches) go straight to the full variant, which keeps medium-long
+        // matches inside the window
+        bool deferred = !FULL && nblk > KZG_EX_BIG_FRAME_BLOCKS;
         for (u32 k = 0; k < nblk && !failed && !deferred; k++) {
             const KzgBlock blk = B.blocks[first + k];
             u8* out = fdst + blk.out_off;
