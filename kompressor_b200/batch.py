@@ -82,7 +82,10 @@ class BatchDecoder:
                 out_offsets[1:] = np.cumsum(capacities)[:-1]
         out_offsets = np.ascontiguousarray(out_offsets, dtype=np.uint64)
         if out is None:
-            out = np.zeros(int(capacities.sum()) if n else 0, dtype=np.uint8)
+            total = sum(int(c) for c in capacities)          # Python integers: a hostile capacity cannot wrap the sum
+            if total >= 1 << 46:
+                raise KzgError("capacities add up to more than any device holds")
+            out = np.zeros(total, dtype=np.uint8)
         status = np.zeros(n, np.uint32)
         out_size = np.zeros(n, np.uint64)
         rc = self._L.kzg_decompress_batch_host(self._h, comp.ctypes.data, offsets.ctypes.data, sizes.ctypes.data,
@@ -108,7 +111,9 @@ class BatchDecoder:
 
         src = torch.zeros(comp.size + pad, dtype=torch.uint8, device=dev)
         src[:comp.size] = torch.from_numpy(comp).to(dev)
-        total_dst = int(caps.sum())
+        total_dst = sum(int(c) for c in caps)
+        if total_dst >= 1 << 46:
+            raise KzgError("capacities add up to more than any device holds")
         return DeviceBatch(src=src, src_off=dev_u64(offsets), src_size=dev_u64(sizes),
                            dst=torch.zeros(total_dst + pad, dtype=torch.uint8, device=dev), dst_off=dev_u64(doff),
                            dst_cap=dev_u64(caps), status=torch.zeros(n, dtype=torch.int32, device=dev),

@@ -20,13 +20,21 @@
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    // Contents are not preserved.  On failure the old buffer (and its capacity) stays as it was, so that a later,
+    // smaller request still works.
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
         const size_t want = bytes + (bytes >> 3) + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
-        cap = want;
+        if (want < bytes) return -1;
+        void* q = nullptr;
+        if (cudaMalloc(&q, want) != cudaSuccess) {
+            cudaGetLastError();
+            // one more try after giving the old buffer back (the request may only fit without it)
+            if (p) { cudaFree(p); p = nullptr; cap = 0; }
+            if (cudaMalloc(&q, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        }
+        if (p) cudaFree(p);
+        p = q; cap = want;
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -129,6 +137,7 @@ extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
     c->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) fprintf(stderr, "kzg: warning: built for sm_100a, device is sm_%d%d\n", prop.major, prop.minor);
+    if (kzg_kernels_init_device(device) != 0) { delete c; return (int)KZG_E_MEMORY; }
     if (cudaMallocHost((void**)&c->h_ctr, KZG_MAX_CHUNKS * sizeof(KzgCounters)) != cudaSuccess) { delete c; return (int)KZG_E_MEMORY; }
     memset(c->h_ctr, 0, KZG_MAX_CHUNKS * sizeof(KzgCounters));
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -275,6 +284,12 @@ static size_t scan_by_seek_table(const u8* p, size_t len, uint64_t* off, uint64_
         if (cs < 4 || pos + cs > tpos) return 0;
         const u32 magic = kzg_rd32(p + pos);
         if (magic != KZG_MAGIC && (magic & 0xFFFFFFF0u) != KZG_SKIP_MAGIC) return 0;
+        if (magic == KZG_MAGIC) {
+            // the table is only a hint (other decoders ignore it): the frame's own header must carry the same content
+            // size, else the block headers are walked as if there were no table
+            KzgFrameHeader h;
+            if (kzg_parse_frame_header(p + pos, (size_t)cs, h) != KZG_OK || h.fcs != ds) return 0;
+        } else if (8ull + kzg_rd32(p + pos + 4) != cs) return 0;
         if (off) off[i] = pos;
         if (size) size[i] = cs;
         if (content) content[i] = magic == KZG_MAGIC ? ds : 0;
@@ -327,7 +342,7 @@ extern "C" size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, ui
             if (type == 3) return (size_t)0 - (size_t)KZG_E_CORRUPTION;
             const u64 adv = type == 1 ? 1 : bsz;
             if (q + 3 + adv > rem) break;
-            bound += type == 2 ? bmax : bsz;
+            bound += type == 2 ? bmax : (bsz < bmax ? bsz : bmax);     // (a raw / RLE block larger than the block maximum is corrupt anyway)
             q += 3 + adv;
             if (bh & 1) { complete = true; break; }
         }
@@ -335,7 +350,10 @@ extern "C" size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, ui
         if (h.has_checksum) { if (q + 4 > rem) break; q += 4; }
         if (off) off[n] = pos;
         if (size) size[n] = q;
-        if (content) content[n] = h.fcs != ~0ull ? h.fcs : bound;
+        // The Frame_Content_Size field is untrusted: a frame cannot regenerate more than its blocks allow, so the
+        // capacity handed out is never larger than that bound (a frame that claims more fails with corruption_detected,
+        // as in libzstd, instead of reserving what it claims).
+        if (content) content[n] = (h.fcs != ~0ull && h.fcs < bound) ? h.fcs : bound;
         n++; pos += (size_t)q;
         if (consumed) *consumed = pos;
     }
@@ -344,24 +362,33 @@ extern "C" size_t kzg_scan_frames(const void* buf, size_t len, uint64_t* off, ui
 
 // ------------------------------------------------------------------------------------------------
 static int ensure_workspace(kzg_ctx* c, u64 n_frames, u64 total_src, u64 total_dst, u64 max_frame_dst) {
+    // wanted sizes first, in locals: the sticky capacities of the context change only when every allocation succeeded
+    u64 block_cap = c->block_cap, lit_cap = c->lit_cap, seq_cap = c->seq_cap;
+    u32 tile_bytes = c->tile_bytes;
     u64 want_blocks = n_frames + (u64)((double)total_dst / c->block_div) + 64;
     if (want_blocks > 0xFFFFFFF0ull) want_blocks = 0xFFFFFFF0ull;
-    if (want_blocks > c->block_cap) { c->block_cap = want_blocks; c->cblock_cap = want_blocks; }
+    if (want_blocks > block_cap) block_cap = want_blocks;
     const u64 want_lit = (u64)((double)total_dst * c->lit_factor) + n_frames * 48 + (1u << 16);
-    if (want_lit > c->lit_cap) c->lit_cap = want_lit;
+    if (want_lit > lit_cap) lit_cap = want_lit;
     const u64 want_seq = (u64)((double)total_dst / c->seq_div) + n_frames * 8 + (1u << 12);
-    if (want_seq > c->seq_cap) c->seq_cap = want_seq;
+    if (want_seq > seq_cap) seq_cap = want_seq;
     u64 blk = max_frame_dst < KZG_BLOCK_MAX ? max_frame_dst : KZG_BLOCK_MAX;
     u32 tile = (u32)((blk + 15) & ~15ull) + 64;
     if (tile < 16384 + 64) tile = 16384 + 64;
-    if (tile > c->tile_bytes) c->tile_bytes = tile;
+    if (tile > tile_bytes) tile_bytes = tile;
     (void)total_src;
-    if (c->frames.ensure(n_frames * sizeof(KzgFrame)) || c->dlist.ensure(n_frames * 4 + 16) || c->blocks.ensure(c->block_cap * sizeof(KzgBlock)) ||
-        c->cblocks.ensure(c->cblock_cap * sizeof(KzgCBlock)) || c->fse.ensure(c->cblock_cap * sizeof(KzgFseDesc)) ||
-        c->huf.ensure(c->cblock_cap * sizeof(KzgHufDesc)) || c->hlist.ensure(c->cblock_cap * 4) ||
-        c->slist.ensure(c->cblock_cap * 4) || c->blist.ensure(c->block_cap * 4) || c->lit.ensure(c->lit_cap + 64) || c->seq.ensure(c->seq_cap * 8) ||
-        c->fsetab.ensure(c->cblock_cap * 2560 + 64))
+    const u64 cblock_cap = block_cap;
+    if (c->frames.ensure(n_frames * sizeof(KzgFrame)) || c->dlist.ensure(n_frames * 4 + 16) || c->blocks.ensure(block_cap * sizeof(KzgBlock)) ||
+        c->cblocks.ensure(cblock_cap * sizeof(KzgCBlock)) || c->fse.ensure(cblock_cap * sizeof(KzgFseDesc)) ||
+        c->huf.ensure(cblock_cap * sizeof(KzgHufDesc)) || c->hlist.ensure(cblock_cap * 4) ||
+        c->slist.ensure(cblock_cap * 4) || c->blist.ensure(block_cap * 4) || c->lit.ensure(lit_cap + 64) || c->seq.ensure(seq_cap * 8) ||
+        c->fsetab.ensure(cblock_cap * 2560 + 64)) {
+        // a request that does not fit must not poison the context: the next (smaller) batch starts from the defaults
+        // again, with whatever buffers survived
+        c->block_cap = c->cblock_cap = 0; c->lit_cap = 0; c->seq_cap = 0;
         return -1;
+    }
+    c->block_cap = block_cap; c->cblock_cap = cblock_cap; c->lit_cap = lit_cap; c->seq_cap = seq_cap; c->tile_bytes = tile_bytes;
     return 0;
 }
 
@@ -491,12 +518,16 @@ extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint
     // extent of the source / destination spans
     u64 src_lo = ~0ull, src_hi = 0, dst_lo = ~0ull, dst_hi = 0, tot_dst = 0;
     for (u64 i = 0; i < n; i++) {
+        // (sizes come from untrusted frame headers further up the stack: no sum may wrap)
+        const u64 se = src_off[i] + src_size[i], de = dst_off[i] + dst_cap[i];
+        if (se < src_off[i] || de < dst_off[i] || tot_dst + dst_cap[i] < tot_dst) return -(int)KZG_E_GENERIC;
         if (src_off[i] < src_lo) src_lo = src_off[i];
-        if (src_off[i] + src_size[i] > src_hi) src_hi = src_off[i] + src_size[i];
+        if (se > src_hi) src_hi = se;
         if (dst_off[i] < dst_lo) dst_lo = dst_off[i];
-        if (dst_off[i] + dst_cap[i] > dst_hi) dst_hi = dst_off[i] + dst_cap[i];
+        if (de > dst_hi) dst_hi = de;
         tot_dst += dst_cap[i];
     }
+    if (src_hi - src_lo > (1ull << 46) || dst_hi - dst_lo > (1ull << 46)) return -(int)KZG_E_MEMORY;     // far beyond any device
     const u64 src_span = src_hi - src_lo, dst_span = dst_hi - dst_lo;
     // device staging: [src span | pad], [dst span], tables: off/size/doff/dcap (u64 each) + out_size (u64) + status (u32)
     const u64 tab_bytes = n * (5 * 8 + 4);

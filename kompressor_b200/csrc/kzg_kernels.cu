@@ -23,6 +23,9 @@
 #include "kzg_fse.cuh"
 #include "kzg_bulk.cuh"
 #include "kzg_exec.cuh"
+#include "kzg_exec2.cuh"
+#include <stdlib.h>
+#include <mutex>
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) kzg_scan_kernel(KzgBatch B) {
@@ -145,21 +148,45 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static bool g_attr_done = false;
-
 const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fsetab", "fse", "huffman", "offsets", "bulk", "execute", "execute_runs", "finish" };
+
+// Which execute kernel runs first: the first design's hot variant (kzg_exec.cuh, lane per sequence), or with KZG_EXEC=2
+// the output-centric second design (kzg_exec2.cuh) and its ring size KZG_EXEC_TILE.  The second design is bit-exact and
+// tested but slower on every corpus measured (profiles/r02_exec2_experiment.txt), so it is not the default.  Read at
+// every launch so that one process can compare them.
+struct KzgExecChoice { int design; u32 tile; };
+static KzgExecChoice kzg_exec_choice() {
+    KzgExecChoice r{ 1, 8192u };
+    if (const char* e = getenv("KZG_EXEC")) r.design = atoi(e) == 2 ? 2 : 1;
+    if (const char* e = getenv("KZG_EXEC_TILE")) { const u32 t = (u32)strtoul(e, nullptr, 10); if (t == 4096u || t == 8192u || t == 16384u || t == 32768u) r.tile = t; }
+    return r;
+}
+
+// Dynamic shared-memory opt-in is per device (per primary context): done once for every device a context is created on.
+int kzg_kernels_init_device(int device) {
+    static std::mutex mu;
+    static u64 done_mask[4] = { 0, 0, 0, 0 };
+    std::lock_guard<std::mutex> lock(mu);
+    if (device >= 0 && device < 256 && (done_mask[device >> 6] >> (device & 63) & 1ull)) return 0;
+    cudaError_t e = cudaSuccess;
+    auto opt = [&](const void* fn, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+    opt((const void*)kzg_huf_kernel, KZG_HUF_SMEM);
+    opt((const void*)kzg_fse_kernel, KZG_FSE_SMEM_TOTAL);
+    opt((const void*)kzg_exec_kernel<false>, KZG_EX_SMEM);
+    opt((const void*)kzg_exec_kernel<true>, KZG_EX_SMEM);
+    opt((const void*)kzg_exec2_kernel<4096>, KZG_X2_WARPS * KzgX2<4096>::BYTES);
+    opt((const void*)kzg_exec2_kernel<8192>, KZG_X2_WARPS * KzgX2<8192>::BYTES);
+    opt((const void*)kzg_exec2_kernel<16384>, KZG_X2_WARPS * KzgX2<16384>::BYTES);
+    opt((const void*)kzg_exec2_kernel<32768>, KZG_X2_WARPS * KzgX2<32768>::BYTES);
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (device >= 0 && device < 256) done_mask[device >> 6] |= 1ull << (device & 63);
+    return 0;
+}
 
 int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
     const size_t huf_smem = KZG_HUF_SMEM;
     const size_t fse_smem = KZG_FSE_SMEM_TOTAL;
     const size_t exec_smem = KZG_EX_SMEM;
-    if (!g_attr_done) {
-        cudaFuncSetAttribute(kzg_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)huf_smem);
-        cudaFuncSetAttribute(kzg_fse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fse_smem);
-        cudaFuncSetAttribute(kzg_exec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exec_smem);
-        cudaFuncSetAttribute(kzg_exec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exec_smem);
-        g_attr_done = true;
-    }
     const u32 n = b.n_frames;
     if (n == 0) return 0;
     int k = 0;
@@ -184,7 +211,18 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
     kzg_bulk_kernel<<<sm_count * 4, KZG_BULK_THREADS, 0, stream>>>(b);
     KZG_MARK();
     const int exec_per_sm = (int)((227 * 1024) / (exec_smem + 1024));
-    kzg_exec_kernel<false><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
+    const KzgExecChoice ch = kzg_exec_choice();
+    if (ch.design == 1) kzg_exec_kernel<false><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
+    else {
+        // one warp per frame, KZG_X2_WARPS per CTA, as many CTAs per SM as the ring size allows
+#define KZG_X2_LAUNCH(T) do { const size_t sm_ = KZG_X2_WARPS * KzgX2<T>::BYTES; const int per_sm_ = (int)((228 * 1024) / (sm_ + 1024)); \
+        kzg_exec2_kernel<T><<<sm_count * (per_sm_ > 16 ? 16 : per_sm_), KZG_X2_WARPS * 32, sm_, stream>>>(b); } while (0)
+        if (ch.tile == 4096u) KZG_X2_LAUNCH(4096);
+        else if (ch.tile == 16384u) KZG_X2_LAUNCH(16384);
+        else if (ch.tile == 32768u) KZG_X2_LAUNCH(32768);
+        else KZG_X2_LAUNCH(8192);
+#undef KZG_X2_LAUNCH
+    }
     KZG_MARK();
     kzg_exec_kernel<true><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);     // deferred frames only
     KZG_MARK();

@@ -280,7 +280,15 @@ struct kzg_DCtx {
     std::vector<uint32_t> status;
     std::vector<uint64_t> osize;
     size_t sticky_error = 0;
+    size_t deferred_error = 0;   // error of a later frame of the same call: reported once the output of the frames before it is delivered
 };
+
+// Most output one call may hold (all frames completed by that call together); beyond it the call fails with
+// memory_allocation instead of reserving whatever a few bytes of RLE blocks can claim.  KZG_STREAM_MAX_OUT_MB overrides.
+static uint64_t stream_max_out() {
+    static const uint64_t v = [] { const char* e = getenv("KZG_STREAM_MAX_OUT_MB"); const uint64_t m = e ? strtoull(e, nullptr, 10) : 0; return (m ? m : 4096ull) << 20; }();
+    return v;
+}
 
 extern "C" kzg_DCtx* kzg_createDCtx(void) {
     if (!g_batcher.ready()) return nullptr;       // no GPU: no decoder (there is no CPU fallback)
@@ -322,7 +330,11 @@ static size_t decode_complete_frames(kzg_DCtx* d, const u8* p, size_t len, size_
             return err(KZG_E_WINDOW_TOO_LARGE);
     }
     uint64_t total = 0, src_total = 0;
-    for (size_t i = 0; i < n; i++) { d->doff[i] = total; total += (d->content[i] + 15) & ~15ull; src_total += d->size[i]; }
+    for (size_t i = 0; i < n; i++) {
+        // (content[i] is bounded by what the frame's blocks can regenerate, see kzg_scan_frames: no sum here can wrap)
+        d->doff[i] = total; total += (d->content[i] + 15) & ~15ull; src_total += d->size[i];
+        if (total > stream_max_out()) return err(KZG_E_MEMORY);
+    }
     // output arena: what is still pending moves to the front of a buffer that also holds the new frames
     const size_t pending = d->out_size - d->out_pos;
     if (pending == 0) { d->out_pos = d->out_size = 0; }
@@ -349,7 +361,15 @@ static size_t decode_complete_frames(kzg_DCtx* d, const u8* p, size_t len, size_
     // compact the outputs (frames were decoded at capacity-spaced offsets)
     size_t w = base;
     for (size_t i = 0; i < n; i++) {
-        if (d->status[i]) return err(d->status[i]);
+        if (d->status[i]) {
+            // libzstd has delivered the frames in front of a bad one by the time it reports the error: keep their
+            // output and report the error when it has been handed over
+            d->out_size = w;
+            *n_frames_out = i;
+            if (w == base && d->out_pos == d->out_size) return err(d->status[i]);
+            d->deferred_error = err(d->status[i]);
+            return consumed;
+        }
         if (w != base + d->doff[i]) memmove(d->out.p + w, d->out.p + base + d->doff[i], d->osize[i]);
         w += d->osize[i];
     }
@@ -393,6 +413,7 @@ extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_i
     }
     const size_t pending = d->out_size - d->out_pos;
     if (pending) return pending;                          // undelivered output: caller must come back with room
+    if (d->deferred_error) { d->sticky_error = d->deferred_error; d->in.clear(); return d->sticky_error; }
     if (!d->in.empty()) return d->in.size() < 9 ? 9 - d->in.size() : 3;   // inside a frame: hint for more input
     if (frames_done || delivered) return 0;               // frame boundary, everything flushed
     return 9;                                             // idle at a frame start (libzstd: header + block header hint)

@@ -12,18 +12,20 @@ _CSRC = os.path.join(_HERE, "..", "..", "kompressor_b200", "csrc")
 
 
 def build():
-    deps = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+    deps = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(_HERE, "simt_emu.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
     if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
         subprocess.check_call(["g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-x", "c++", "-Wall", "-Wno-unknown-pragmas",
-                               "-o", _SO, os.path.join(_HERE, "hostsim.cpp")])
+                               "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-I", _HERE, "-o", _SO, os.path.join(_HERE, "hostsim.cpp")])
     return _SO
 
 
 _lib = None
 
 
-def run(frames, caps):
-    """Decodes `frames` (list of bytes) with the host-compiled stage code -> (outputs, status, sizes)."""
+def run(frames, caps, exec_mode: int = 0, tile: int = 8192):
+    """Decodes `frames` (list of bytes) with the host-compiled stage code -> (outputs, status, sizes).
+    exec_mode 0: sequential execute stand-in; 1 / 2: the second execute design (kzg_exec2.cuh) on the lock-step warp
+    emulator with lanes scheduled in forward / reverse order, ring size `tile`."""
     global _lib
     if _lib is None:
         _lib = ctypes.CDLL(build())
@@ -31,6 +33,10 @@ def run(frames, caps):
                                               ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                               ctypes.c_void_p, ctypes.c_uint64]
+    _lib.kzs_set_exec.argtypes = [ctypes.c_int, ctypes.c_uint32]
+    _lib.kzs_set_exec.restype = None
+    _lib.kzs_exec_deferred.restype = ctypes.c_uint64
+    _lib.kzs_set_exec(exec_mode, tile)
     n = len(frames)
     blob = b"".join(frames)
     comp = np.frombuffer(blob, dtype=np.uint8).copy() if blob else np.zeros(1, np.uint8)

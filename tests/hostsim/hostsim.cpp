@@ -4,7 +4,9 @@
 // sequence-record format can be checked against libzstd without a GPU.  The execute step below is
 // a simple sequential stand-in for the CUDA execute kernel (which is warp-cooperative and only
 // testable on a GPU).  Never linked into libkzg.so.
+#define KZG_SIMT_EMU 1
 #include "../../kompressor_b200/csrc/kzg_stages.cuh"
+#include "../../kompressor_b200/csrc/kzg_exec2.cuh"      // the second execute design, run on the lock-step warp emulator (simt_emu.h)
 
 #include <stdlib.h>
 #include <string.h>
@@ -29,6 +31,42 @@ static u64 xxh64(const u8* p, u64 len) {
     while (p < end) { h = rotl(h ^ ((u64)(*p) * P5), 11) * P1; p++; }
     h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
     return h;
+}
+
+// Execute step: 0 = sequential stand-in, 1 / 2 = kzg_exec2_block on the warp emulator (lanes scheduled in forward /
+// reverse order), with the ring size TILE.  What kzg_bulk_kernel does is done sequentially first, as on the GPU.
+static int g_exec_mode = 0;
+static u32 g_exec_tile = 8192;
+static u64 g_exec_deferred = 0, g_exec_collectives = 0;
+extern "C" void kzs_set_exec(int mode, u32 tile) { g_exec_mode = mode; g_exec_tile = tile; }
+extern "C" u64 kzs_exec_deferred() { return g_exec_deferred; }
+
+struct X2Arg { const KzgBatch* B; u32 frame; u32 result; };
+template <u32 TILE> static void x2_lane(void* p, u32 lane) {
+    X2Arg* A = (X2Arg*)p;
+    const KzgBatch& B = *A->B;
+    const KzgFrame* fr = &B.frames[A->frame];
+    u8* const fdst = B.dst + B.dst_off[A->frame];
+    u32 r = 0;
+    for (u32 k = 0; k < fr->n_blocks && r == 0; k++) {
+        const KzgBlock blk = B.blocks[fr->first_block + k];
+        if (blk.type != 2) continue;
+        const KzgCBlock* cb = &B.cblocks[blk.cidx];
+        if (cb->n_seq == 0) continue;
+        if (cb->bulk_lits) { r = 2; break; }
+        r = kzg_exec2_block<TILE>(B, blk, cb, fdst + blk.out_off, simt::Warp::SMEM_BASE, lane);
+    }
+    if (lane == 0) A->result = r;
+}
+static u32 x2_run_frame(const KzgBatch& B, u32 f) {
+    X2Arg A{ &B, f, 0 };
+    const bool rev = g_exec_mode == 2;
+    switch (g_exec_tile) {
+        case 4096: simt::run_warp(x2_lane<4096>, &A, KzgX2<4096>::BYTES, rev); break;
+        case 16384: simt::run_warp(x2_lane<16384>, &A, KzgX2<16384>::BYTES, rev); break;
+        default: simt::run_warp(x2_lane<8192>, &A, KzgX2<8192>::BYTES, rev); break;
+    }
+    return A.result;
 }
 
 extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* src_off, const u64* src_size, u64 n,
@@ -95,7 +133,26 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
         KzgFrame& fr = frames[f];
         u32 st = fr.status;
         u8* fdst = dst + dst_off[f];
-        for (u32 k = 0; !st && k < fr.n_blocks; k++) {
+        bool emulated = false;
+        if (g_exec_mode != 0 && !st) {
+            // what kzg_bulk_kernel writes (kzg_bulk.cuh), then the warp-emulated execute kernel
+            for (u32 k = 0; k < fr.n_blocks; k++) {
+                const KzgBlock& blk = blocks[fr.first_block + k];
+                u8* out = fdst + blk.out_off;
+                if (blk.type == 0) { memcpy(out, src + blk.src, blk.regen); continue; }
+                if (blk.type == 1) { memset(out, src[blk.src], blk.regen); continue; }
+                const KzgCBlock& cb = cblocks[blk.cidx];
+                const u8* l = cb.lit_type >= 2 ? B.lit_pool + cb.lit_out : src + cb.src + cb.lit_src;
+                if (cb.n_seq == 0) { if (cb.lit_type == 1) memset(out, l[0], blk.regen); else memcpy(out, l, blk.regen); continue; }
+                const u32 trail = cb.lit_regen - cb.lit_used;
+                if (trail >= KZG_BULK_MIN) { if (cb.lit_type == 1) memset(out + blk.regen - trail, l[0], trail); else memcpy(out + blk.regen - trail, l + cb.lit_used, trail); }
+            }
+            const u32 r = x2_run_frame(B, f);
+            if (r == 1) st = KZG_E_CORRUPTION;
+            else if (r == 2) g_exec_deferred++;
+            else emulated = true;
+        }
+        for (u32 k = 0; !st && !emulated && k < fr.n_blocks; k++) {
             const KzgBlock& blk = blocks[fr.first_block + k];
             u8* out = fdst + blk.out_off;
             if (blk.type == 0) memcpy(out, src + blk.src, blk.regen);

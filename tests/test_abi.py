@@ -154,3 +154,49 @@ def test_seek_table_with_checksum_entries(kzg_lib, libzstd):
     bad = body + table[:-5] + bytes([0x84]) + table[-4:]
     off2, size2, _, _ = scan_frames(bad)
     assert len(off2) == 6 and [int(x) for x in size2[:5]] == [len(f) for f in frames]
+
+
+def test_scan_frames_bounds_a_hostile_content_size(kzg_lib, libzstd):
+    """Frame_Content_Size is untrusted: a 17-byte frame that claims 2^64 - 2 bytes in front of a valid frame
+    must not wrap any capacity arithmetic -- the capacity handed out is bounded by what the frame's blocks can
+    regenerate, so the frame later fails like in libzstd (FCS larger than the decoded size -> corruption_detected)."""
+    import struct
+    from kompressor_b200.batch import scan_frames
+    hostile = struct.pack("<IB", 0xFD2FB528, 0xE0) + struct.pack("<Q", 0xFFFFFFFFFFFFFFFE) + bytes([0x01, 0x00, 0x00])   # single segment, 8-byte FCS, empty last raw block
+    good_raw = bytes(range(256)) * 40
+    good = libzstd.compress(good_raw, 3)
+    off, size, content, consumed = scan_frames(hostile + good)
+    assert consumed == len(hostile) + len(good) and len(off) == 2
+    assert int(size[0]) == len(hostile) and int(content[0]) == 0          # its only block regenerates nothing
+    assert int(content[1]) == len(good_raw)
+    out, err = libzstd.decompress_oneshot(hostile, 64)
+    assert err == 20
+    # an RLE block cannot claim more than the block maximum either (4 bytes of input, 2 MiB claimed)
+    rle = struct.pack("<IB", 0xFD2FB528, 0x20) + bytes([0x00]) + struct.pack("<I", 1 | (1 << 1) | (0x1FFFFF << 3))[:3] + b"x"
+    _, _, c3, _ = scan_frames(rle)
+    assert int(c3[0]) <= 128 * 1024
+
+
+def test_seek_table_is_only_a_hint(kzg_lib, libzstd):
+    """A stale seek table (sizes that do not match the frames' own headers) must not change what is decoded: libzstd
+    ignores skippable frames, so the block headers are walked as if the table were not there."""
+    import struct
+    from kompressor_b200.batch import scan_frames
+    raws = [bytes([97 + i]) * (500 + 100 * i) + bytes(range(200)) for i in range(4)]
+    frames = [libzstd.compress(r, 3) for r in raws]
+    body = b"".join(frames)
+
+    def table(entries):
+        e = b"".join(struct.pack("<II", c, d) for c, d in entries)
+        return struct.pack("<II", 0x184D2A5E, len(e) + 9) + e + struct.pack("<IBI", len(entries), 0, 0x8F92EAB1)
+
+    honest = [(len(f), len(r)) for f, r in zip(frames, raws)]
+    understated = [(c, d - 1 if i == 2 else d) for i, (c, d) in enumerate(honest)]
+    merged = [honest[0], (honest[1][0] + honest[2][0], honest[1][1] + honest[2][1]), honest[3]]
+    for entries in (understated, merged):
+        off, size, content, consumed = scan_frames(body + table(entries))
+        assert len(off) == 5 and consumed == len(body) + len(table(entries))
+        assert [int(x) for x in size[:4]] == [len(f) for f in frames]
+        assert [int(x) for x in content[:4]] == [len(r) for r in raws]
+    off, size, content, _ = scan_frames(body + table(honest))
+    assert [int(x) for x in content[:4]] == [len(r) for r in raws]

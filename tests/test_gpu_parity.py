@@ -205,3 +205,61 @@ def test_device_resident_batch_and_size_independent_properties(dec):
     assert h_got == h_exp
     st = dec.stats()
     assert st.n_cblocks == n and st.launches == 11
+
+
+def test_hostile_content_size_does_not_reach_the_allocator(dec, libzstd):
+    """a 17-byte frame claiming 2^64 - 2 bytes in front of a valid 1 MiB frame.  With the capacities
+    kzg_scan_frames hands out, the hostile frame fails (corruption_detected, as in libzstd) and the valid one decodes;
+    capacities that wrap are refused by the host entry point instead of reaching device memory."""
+    import struct
+    from kompressor_b200 import KzgError
+    from kompressor_b200.batch import scan_frames
+    import corpus
+    hostile = struct.pack("<IB", 0xFD2FB528, 0xE0) + struct.pack("<Q", 0xFFFFFFFFFFFFFFFE) + bytes([0x01, 0x00, 0x00])
+    raw = bytes(corpus.generate("logs", 31, 1 << 20))
+    good = libzstd.compress(raw, 3)
+    blob = hostile + good
+    off, size, content, _ = scan_frames(blob)
+    comp = np.frombuffer(blob, np.uint8).copy()
+    out, doff, status, osz = dec.decompress_host(comp, off, size, content)
+    assert int(status[0]) == 20 and int(status[1]) == 0
+    assert bytes(out[int(doff[1]):int(doff[1] + osz[1])]) == raw
+    with pytest.raises(KzgError):       # the wrapping capacity itself: refused before any device arithmetic
+        dec.decompress_host(comp, off, size, np.array([0xFFFFFFFFFFFFFFF0, len(raw)], np.uint64),
+                            out=np.zeros(len(raw) + 64, np.uint8), out_offsets=np.array([0, 0], np.uint64))
+    # the context is still usable afterwards (ADVICE r1, medium: a failed sizing must not stick)
+    outs, status, _ = run(dec, [good], [len(raw)])
+    assert status[0] == 0 and outs[0] == raw
+
+
+@pytest.mark.parametrize("tile", ["4096", "8192", "32768"])
+def test_second_execute_design_is_bit_exact(dec, libzstd, tile, monkeypatch):
+    """kzg_exec2.cuh (output-centric execute, ring window, bulk flush) is selectable with KZG_EXEC=2; it must give the
+    same bytes as the default kernel on every corpus kind, on runs, long far matches and multi-block level-19 frames."""
+    import corpus
+    monkeypatch.setenv("KZG_EXEC", "2")
+    monkeypatch.setenv("KZG_EXEC_TILE", tile)
+    rng = np.random.default_rng(3)
+    raws = []
+    for kind in ("logs", "json", "literal"):
+        raws += [bytes(corpus.generate(kind, 50 + i, 65536)) for i in range(24)]
+    raws += [bytes(40000), b"abc" * 20000, bytes(rng.integers(0, 3, 70000, dtype=np.uint8))]
+    a = bytes(corpus.generate("logs", 9, 50000))
+    raws.append(a + a[::-1] + a)
+    raws += [bytes(corpus.generate("mixed", 70 + i, 700000)) for i in range(2)]
+    frames = [libzstd.compress(r, 19 if len(r) > 200000 else 3, checksum=bool(i & 1), pledged=bool(i & 2)) for i, r in enumerate(raws)]
+    outs, status, _ = run(dec, frames, [len(r) + (i % 5) for i, r in enumerate(raws)])
+    assert (status == 0).all()
+    assert outs == raws
+
+
+def test_configs4_exact_shape(dec, libzstd):
+    """BASELINE.json configs[4]: one 4 MiB frame, 2 MiB log text + 2 MiB JSON lines, level 19, streamed (window
+    descriptor, 8 MiB window, no content size), cross-block history and long offsets."""
+    import corpus
+    c = corpus.build("mixed", 2, 4 << 20, 19, False, streamed=True)
+    frames = frames_of(c)
+    assert frames[0][4] & 0x20 == 0                       # not single-segment: a window descriptor follows
+    outs, status, sizes = run(dec, frames, [4 << 20] * 2)
+    assert (status == 0).all() and (sizes == 4 << 20).all()
+    assert hashlib.sha256(b"".join(outs)).digest() == hashlib.sha256(c.raw.tobytes()).digest()

@@ -235,3 +235,27 @@ def test_sampleRoundtripKotlinxIoSink(api, libzstd):    # ZstdTest.kt:40-47: com
         io.transferTo(libzstd.compress(data, 3, checksum=True), sink)
         sink.close()
         assert output.readByteArray() == data
+
+
+def test_frames_before_a_bad_frame_are_delivered_first(api, libzstd):
+    """libzstd hands over the output of the frames in front of a corrupt one before it reports the error:
+    the shim decodes all complete frames of a call as one batch and must behave the same."""
+    import corpus
+    core, _, zstd = api
+    raws = [bytes(corpus.generate("logs", 600 + i, 30000)) for i in range(4)]
+    frames = [bytearray(libzstd.compress(r, 3, checksum=True)) for r in raws]
+    frames[2][len(frames[2]) // 2] ^= 0x10
+    blob = b"".join(bytes(f) for f in frames)
+    d = zstd.ZstdDecompressor()
+    inp = core.ByteArraySlice(bytearray(blob))
+    inp.writeStart = len(blob)
+    got = bytearray()
+    with pytest.raises(zstd.IllegalStateException) as ei:
+        while True:
+            o = core.ByteArraySlice(8192)
+            d.transform(inp, o, True)
+            got += o.data[o.readStart:o.writeStart]
+            if not (inp.hasData or o.insufficient):
+                break
+    assert ei.value.code in (20, 22)
+    assert bytes(got) == raws[0] + raws[1]
