@@ -48,7 +48,7 @@ struct kzg_ctx {
     int device = 0;
     int sm_count = 0;
     std::mutex mu;
-    DevBuf frames, blocks, cblocks, fse, huf, hlist, slist, blist, dlist, lit, seq, fsetab, ctr, consts;
+    DevBuf frames, blocks, cblocks, fse, huf, hlist, hlist2, slist, blist, dlist, lit, seq, fsetab, ctr, consts;
     // sizing state (sticky across batches, grown on overflow)
     u64 block_cap = 0, cblock_cap = 0, lit_cap = 0, seq_cap = 0;
     u32 tile_bytes = 0;
@@ -165,7 +165,7 @@ extern "C" int kzg_ctx_create(kzg_ctx** out, int device) {
 extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* all[] = { &c->frames, &c->blocks, &c->cblocks, &c->fse, &c->huf, &c->hlist, &c->slist, &c->blist, &c->dlist, &c->lit, &c->seq, &c->fsetab,
+    DevBuf* all[] = { &c->frames, &c->blocks, &c->cblocks, &c->fse, &c->huf, &c->hlist, &c->hlist2, &c->slist, &c->blist, &c->dlist, &c->lit, &c->seq, &c->fsetab,
                       &c->ctr, &c->consts, &c->st_src, &c->st_dst, &c->st_tab, &c->dict };
     for (DevBuf* b : all) b->release();
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -380,7 +380,7 @@ static int ensure_workspace(kzg_ctx* c, u64 n_frames, u64 total_src, u64 total_d
     const u64 cblock_cap = block_cap;
     if (c->frames.ensure(n_frames * sizeof(KzgFrame)) || c->dlist.ensure(n_frames * 4 + 16) || c->blocks.ensure(block_cap * sizeof(KzgBlock)) ||
         c->cblocks.ensure(cblock_cap * sizeof(KzgCBlock)) || c->fse.ensure(cblock_cap * sizeof(KzgFseDesc)) ||
-        c->huf.ensure(cblock_cap * sizeof(KzgHufDesc)) || c->hlist.ensure(cblock_cap * 4) ||
+        c->huf.ensure(cblock_cap * sizeof(KzgHufDesc)) || c->hlist.ensure(cblock_cap * 4) || c->hlist2.ensure(cblock_cap * 4) ||
         c->slist.ensure(cblock_cap * 4) || c->blist.ensure(block_cap * 4) || c->lit.ensure(lit_cap + 64) || c->seq.ensure(seq_cap * 8) ||
         c->fsetab.ensure(cblock_cap * 2560 + 64)) {
         // a request that does not fit must not poison the context: the next (smaller) batch starts from the defaults
@@ -408,7 +408,7 @@ static int enqueue_batch(kzg_ctx* c, const void* d_src, const uint64_t* d_src_of
     b.tile_bytes = c->tile_bytes;
     b.frames = (KzgFrame*)c->frames.p; b.blocks = (KzgBlock*)c->blocks.p; b.cblocks = (KzgCBlock*)c->cblocks.p;
     b.fse = (KzgFseDesc*)c->fse.p; b.huf = (KzgHufDesc*)c->huf.p;
-    b.hlist = (u32*)c->hlist.p; b.slist = (u32*)c->slist.p; b.blist = (u32*)c->blist.p; b.dlist = (u32*)c->dlist.p;
+    b.hlist = (u32*)c->hlist.p; b.hlist2 = (u32*)c->hlist2.p; b.slist = (u32*)c->slist.p; b.blist = (u32*)c->blist.p; b.dlist = (u32*)c->dlist.p;
     b.lit_pool = (u8*)c->lit.p; b.seq_pool = (u64*)c->seq.p; b.fse_tab = (u16*)c->fsetab.p;
     b.ctr = (KzgCounters*)c->ctr.p;
     b.fse_default = (const KzgFseDesc*)((const u8*)c->consts.p + offsetof(KzgConsts, def));

@@ -143,6 +143,7 @@ struct KzgCounters {
     u32 n_bulk;             // entries of blist
     u32 n_defer;            // entries of dlist
     u32 ticket_exec2;
+    u32 n_hblocks2, ticket_huf2;   // Huffman blocks whose table does not fit the compact two-level layout (second launch)
 };
 
 #define KZG_INVALID_OWNER 0xFFFFFFFEu
@@ -167,6 +168,7 @@ struct KzgBatch {
     KzgFseDesc* fse;
     KzgHufDesc* huf;
     u32* hlist;         // compressed blocks with Huffman-coded literals
+    u32* hlist2;        // ... of those, the ones left to the second Huffman launch (worst-case table layout)
     u32* slist;         // compressed blocks with sequences
     u32* blist;         // blocks with work for the bulk kernel (filled by the offsets stage)
     u32* dlist;         // frames the hot execute kernel left to the full one (long runs)

@@ -101,30 +101,60 @@ KZG_HD void kzg_huf_build_phase2(KzgHufScratch* sc, u32 maxbits, u32 lane) {
     }
 }
 
-KZG_HD void kzg_huf_build_phase3(u16* tab, KzgHufScratch* sc, u32 nsym, u32 maxbits, u32 lane) {
+// Two-level table.  The full table would have 2^maxbits entries (4 KiB at 11 bits), which limits how many blocks an
+// SM can decode at once.  The canonical order puts the longest codes first, so the entries of the codes longer than
+// KZG_HUF_L1_BITS are exactly the first X entries of the full table (X = sum over the weights w <= sshift of
+// count_w * 2^(w-1), a multiple of 2^sshift by the Kraft equality) and every other code covers whole groups of 2^sshift
+// entries.  Stored are therefore
+//   l2[0, X)                       = the first X entries of the full table (long codes), and
+//   l1[0, 2^(maxbits - sshift))    = one entry per group of 2^sshift (short codes; the groups below X >> sshift unused),
+// and a lookup is ONE load: index idx (the next maxbits bits) reads l2[idx] if idx < X, else l1[idx >> sshift].
+// At most 1 KiB + 2 * X bytes per table; on text X is a few dozen.
+// With l1bits = KZG_HUF_MAXBITS the first level is the full table, X = 0 and the second level is empty: the layout of
+// the launch that takes the blocks with long streams (there the chain latency per symbol counts, not the footprint).
+#define KZG_HUF_L1_BITS 9
+KZG_HD u32 kzg_huf_split(u32 maxbits, u32 l1bits = KZG_HUF_L1_BITS) { return maxbits > l1bits ? maxbits - l1bits : 0u; }
+
+// (after phase 1) entries of the full table that belong to codes longer than l1bits
+KZG_HD u32 kzg_huf_long_entries(const KzgHufScratch* sc, u32 maxbits, u32 l1bits = KZG_HUF_L1_BITS) {
+    const u32 sshift = kzg_huf_split(maxbits, l1bits);
+    u32 x = 0;
+    for (u32 w = 1; w <= sshift; w++) x += ((u32)sc->cnt[0][w] + sc->cnt[1][w] + sc->cnt[2][w] + sc->cnt[3][w]) << (w - 1);
+    return x;
+}
+
+KZG_HD void kzg_huf_build_phase3(u16* l1, u16* l2, KzgHufScratch* sc, u32 nsym, u32 maxbits, u32 lane, u32 l1bits = KZG_HUF_L1_BITS) {
     const u32 lo = 64 * lane, hi = nsym < lo + 64 ? nsym : lo + 64;
+    const u32 sshift = kzg_huf_split(maxbits, l1bits);
     for (u32 s = lo; s < hi; s++) {
         const u32 w = sc->w[s];
         if (w == 0 || w > maxbits) continue;
         const u32 span = 1u << (w - 1), p = sc->st[lane][w];
         sc->st[lane][w] = (u16)(p + span);
         const u32 e = s | ((maxbits + 1 - w) << 8);
-        if (span == 1) { tab[p] = (u16)e; continue; }
+        if (w <= sshift) {                       // a long code: 1 or 2 entries of the second level
+            l2[p] = (u16)e;
+            if (span == 2) l2[p + 1] = (u16)e;
+            continue;
+        }
+        const u32 q = p >> sshift, n = span >> sshift;       // naturally aligned run of n = 2^k first-level entries
+        if (n == 1) { l1[q] = (u16)e; continue; }
         const u32 e2 = e | (e << 16);
-        u32* t32 = reinterpret_cast<u32*>(tab) + (p >> 1);
-        for (u32 k = 0; k < (span >> 1); k++) t32[k] = e2;
+        u32* t32 = reinterpret_cast<u32*>(l1) + (q >> 1);
+        for (u32 k = 0; k < (n >> 1); k++) t32[k] = e2;
     }
 }
 
 // One Huffman stream: decodes exactly n symbols from [src, src+size) into dst. Returns 0 or an error.
-KZG_HD u32 kzg_huf_decode_stream(const u8* src, u32 size, const u16* tab, u32 maxbits, u8* dst, u32 n) {
+KZG_HD u32 kzg_huf_decode_stream(const u8* src, u32 size, const u16* l1, const u16* l2, u32 nlong, u32 maxbits, u8* dst, u32 n) {
     KzgBwdQ b;
     if (!b.init(src, size)) return KZG_E_CORRUPTION;
-    const u32 shift = 64 - maxbits;
+    const u32 shift = 64 - maxbits, sshift = kzg_huf_split(maxbits);
     u32 i = 0;
 #define KZG_HUF_SYM(out)                                   \
     {                                                      \
-        const u32 e = tab[(u32)(b.win >> shift)];          \
+        const u32 idx = (u32)(b.win >> shift);             \
+        const u32 e = idx < nlong ? l2[idx] : l1[idx >> sshift]; \
         b.skip(e >> 8);                                    \
         out = e & 255u;                                    \
     }

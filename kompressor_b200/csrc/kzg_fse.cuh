@@ -45,8 +45,13 @@
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
 // One more warp rides along in every CTA and decodes Huffman literals (kzg_huf_warp_loop) in the shared memory and
 // the issue slots the four sequence warps leave free; it stops taking work when both pairs of its CTA are done.
-#define KZG_FSE_THREADS (KZG_FSE_WARPS * 32 + 64)           // warp 4 is empty: warp 5 shares a scheduler with a post warp, not a chain warp
-#define KZG_FSE_SMEM_TOTAL (KZG_FSE_SMEM + KZG_HUF_WARP_SMEM)
+// Literal warps are the odd warps 5, 7, ... (the even ones in between exit at once): they share a scheduler with a post
+// warp, not with a chain warp.  With the two-level Huffman tables a literal warp needs 13 KiB, so up to three fit.
+#define KZG_FSE_LIT_WARPS_MAX 3
+#define KZG_FSE_THREADS_OF(nlit) (KZG_FSE_WARPS * 32 + 64 * (nlit))
+#define KZG_FSE_THREADS KZG_FSE_THREADS_OF(KZG_FSE_LIT_WARPS_MAX)
+#define KZG_FSE_SMEM_TOTAL_OF(nlit) (KZG_FSE_SMEM + (nlit) * KZG_HUF_WARP_SMEM)
+#define KZG_FSE_SMEM_TOTAL KZG_FSE_SMEM_TOTAL_OF(KZG_FSE_LIT_WARPS_MAX)
 #define KZG_FSE_DONE_WORD 127                               // in the code-word area: pairs of this CTA that have finished
 #ifndef KZG_FSE_WIDE_LIMIT
 #define KZG_FSE_WIDE_LIMIT 32u                              // most extra bits per sequence the fast loop extracts (tests lower it)
@@ -186,11 +191,11 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
     const bool chain = (warp & 1u) == 0;                   // even warp: chain, odd warp: post
     for (u32 k = threadIdx.x; k < KZG_FSE_CODE_WORDS; k += blockDim.x) llx[k] = k < 89 ? B.code_tables[k] : 0u;
     __syncthreads();
-    if (warp == KZG_FSE_WARPS) return;
-    if (warp > KZG_FSE_WARPS) {                             // the literal warp
+    if (warp >= KZG_FSE_WARPS && !(warp & 1u)) return;
+    if (warp > KZG_FSE_WARPS) {                             // a literal warp
         // only where the sequence work lasts long enough to hide a ticket (8 blocks of literals) behind it
         if (B.ctr->seq_used < (u64)B.ctr->n_sblocks * 1024u) return;
-        kzg_huf_warp_loop(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_SMEM, lane, reinterpret_cast<volatile u32*>(llx + KZG_FSE_DONE_WORD), KZG_FSE_PAIRS);
+        kzg_huf_warp_loop<KZG_HUF_L1_BITS, KZG_HUF_L2CAP, false>(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_SMEM + ((warp - KZG_FSE_WARPS - 1u) >> 1) * KZG_HUF_WARP_SMEM, lane, reinterpret_cast<volatile u32*>(llx + KZG_FSE_DONE_WORD), KZG_FSE_PAIRS);
         return;
     }
     const u32 s_llx = smem_addr(llx), s_mlx = s_llx + 36 * 4;

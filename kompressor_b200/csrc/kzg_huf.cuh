@@ -3,7 +3,14 @@
 //
 // Like the sequence kernel this is a serial chain per stream (window -> table entry -> code length ->
 // shifted window), so the loop is kept short and free of divergence:
-//   * the four lanes of a block build its 2^maxbits-entry table together in shared memory (4 KiB);
+//   * the four lanes of a block build its table together in shared memory.  The table is two-level (kzg_entropy.cuh:
+//     512 first-level entries + the few dozen full-table entries of the codes longer than 9 bits, ONE load per symbol
+//     either way): 1.1 KiB per block instead of 4 KiB, so an SM holds 128 blocks instead of 48 and the 16 384 blocks of
+//     a 1 GiB batch decode in one wave instead of three (the kernel is bound by the latency of the chain, i.e. by how
+//     many chains are in flight).  Blocks with long streams (>= 32 KiB of literals: literal-heavy data, where few
+//     chains exist anyway and every cycle of the chain counts) and blocks whose codes need more second-level entries
+//     than the compact layout holds (never seen outside crafted input) are left to a second launch with full
+//     single-level tables;
 //   * each lane's backward bitstream is staged by cp.async (LDGSTS: no destination register, no per-warp
 //     scoreboard stall) into a 128-byte ring, serviced at warp-uniform points once per 16 symbols;
 //   * a 64-bit window is re-read from the ring every 4 symbols (3 LDS + 2 funnel shifts, 4 x 11 bits fit),
@@ -15,10 +22,13 @@
 #include "kzg_stages.cuh"
 
 #define KZG_HUF_WARPS 2
-#define KZG_HUF_TAB_BYTES ((1u << KZG_HUF_MAXBITS) * 2u)
+#define KZG_HUF_L2CAP 64u                                    // second-level entries per block, compact layout
+#define KZG_HUF_LONG_STREAMS 32768u                          // blocks with at least this many literals go to the full-table launch
 #define KZG_HUF_RING_BYTES (32u * 128u)                      // per warp: 32 lanes x 8 chunks x 16 B
-#define KZG_HUF_WARP_SMEM (8u * KZG_HUF_TAB_BYTES + KZG_HUF_RING_BYTES)
+#define KZG_HUF_WARP_SMEM_OF(l1bits, l2cap) (8u * ((2u << (l1bits)) + 2u * (l2cap)) + KZG_HUF_RING_BYTES)
+#define KZG_HUF_WARP_SMEM KZG_HUF_WARP_SMEM_OF(KZG_HUF_L1_BITS, KZG_HUF_L2CAP)
 #define KZG_HUF_SMEM (KZG_HUF_WARPS * KZG_HUF_WARP_SMEM)
+#define KZG_HUF_SMEM_FULL (KZG_HUF_WARPS * KZG_HUF_WARP_SMEM_OF(KZG_HUF_MAXBITS, 0u))
 
 static_assert(sizeof(KzgHufScratch) <= 4 * 128, "table-build scratch must fit the rings of a block's four lanes");
 
@@ -41,38 +51,52 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 // The work loop of one warp (wbase: its KZG_HUF_WARP_SMEM bytes of shared memory).  With `stop` set, the warp takes no
 // new ticket once *stop reaches stop_at: that is how the warp that rides along in the sequence kernel (kzg_fse.cuh)
 // leaves when the sequence work of its SM is done; kzg_huf_kernel then finishes what is left.
+// L1BITS / L2CAP: first-level index width and second-level entries per block in this warp's layout; SECOND: the launch
+// that takes the blocks the compact launch left (work list hlist2), with L1BITS = KZG_HUF_MAXBITS (full tables).
+template <u32 L1BITS, u32 L2CAP, bool SECOND>
 __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, u32 lane, const volatile u32* stop, u32 stop_at) {
     using namespace kzg_huf;
     const u32 hb = lane >> 2, st = lane & 3;
-    u16* tab = reinterpret_cast<u16*>(wbase + hb * KZG_HUF_TAB_BYTES);
-    KzgHufScratch* sc = reinterpret_cast<KzgHufScratch*>(wbase + 8u * KZG_HUF_TAB_BYTES + hb * 512u);   // = the block's four rings
-    const u32 s_tab = (u32)__cvta_generic_to_shared(tab);
-    const u32 s_ring = (u32)__cvta_generic_to_shared(wbase + 8u * KZG_HUF_TAB_BYTES) + (lane << 7);
+    constexpr u32 L1_BYTES = 2u << L1BITS;
+    u16* l1 = reinterpret_cast<u16*>(wbase + hb * L1_BYTES);
+    u16* l2 = reinterpret_cast<u16*>(wbase + 8u * L1_BYTES + hb * (2u * L2CAP));
+    u8* const rings = wbase + 8u * (L1_BYTES + 2u * L2CAP);
+    KzgHufScratch* sc = reinterpret_cast<KzgHufScratch*>(rings + hb * 512u);   // = the block's four rings
+    const u32 s_l1 = (u32)__cvta_generic_to_shared(l1), s_l2 = (u32)__cvta_generic_to_shared(l2);
+    const u32 s_ring = (u32)__cvta_generic_to_shared(rings) + (lane << 7);
     if (B.ctr->overflow & 3u) return;
-    const u32 n = B.ctr->n_hblocks;
+    const u32 n = SECOND ? B.ctr->n_hblocks2 : B.ctr->n_hblocks;
+    const u32* list = SECOND ? B.hlist2 : B.hlist;
     for (;;) {
         u32 g = 0xFFFFFFFFu;
-        if (lane == 0 && !(stop && *stop >= stop_at)) g = atomicAdd(&B.ctr->ticket_huf, 1u);
+        if (lane == 0 && !(stop && *stop >= stop_at)) g = atomicAdd(SECOND ? &B.ctr->ticket_huf2 : &B.ctr->ticket_huf, 1u);
         g = __shfl_sync(0xFFFFFFFFu, g, 0);
         if (g == 0xFFFFFFFFu || (u64)g * 8 >= n) break;
         const u32 h = g * 8 + hb;
         bool valid = h < n;
         KzgCBlock* cb = nullptr;
         if (valid) {
-            cb = &B.cblocks[B.hlist[h]];
+            cb = &B.cblocks[list[h]];
             valid = cb->status_lit == KZG_OK && cb->huf_owner != KZG_INVALID_OWNER;
         }
         // ---- table: built by the block's four lanes (the rings serve as scratch until the streams start)
-        u32 maxbits = KZG_HUF_MAXBITS, nsym = 0;
+        u32 maxbits = KZG_HUF_MAXBITS, nsym = 0, nlong = 0;
         if (valid) {
             const KzgHufDesc* hd = kzg_huf_desc_of(B, cb->huf_owner);
             maxbits = hd->maxbits; nsym = hd->nsym;
             kzg_huf_build_phase1(sc, hd->weight, nsym, st);
         }
         __syncwarp();
+        if (valid) {
+            nlong = kzg_huf_long_entries(sc, maxbits, L1BITS);
+            if (nlong > L2CAP || (!SECOND && cb->lit_regen >= KZG_HUF_LONG_STREAMS)) {      // left to the full-table launch
+                if (!SECOND && st == 0) B.hlist2[atomicAdd(&B.ctr->n_hblocks2, 1u)] = list[h];
+                valid = false;
+            }
+        }
         if (valid) kzg_huf_build_phase2(sc, maxbits, st);
         __syncwarp();
-        if (valid) kzg_huf_build_phase3(tab, sc, nsym, maxbits, st);
+        if (valid) kzg_huf_build_phase3(l1, l2, sc, nsym, maxbits, st, L1BITS);
         __syncwarp();
 
         // ---- this lane's stream
@@ -109,7 +133,7 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         cp_commit();
         cp_wait<0>();
         ready_lo = pend1 = pend2 = next_c + 1;
-        const u32 sh = 32u - maxbits;
+        const u32 sh = 32u - maxbits, sshift = kzg_huf_split(maxbits, L1BITS);
 
 #define KZG_HUF_WINDOW(hi, lo)                                                     \
         {                                                                          \
@@ -139,7 +163,8 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         // one symbol from the top of hi:lo; advances the window and `used`
 #define KZG_HUF_SYM(sym, hi, lo, used)                                             \
         {                                                                          \
-            const u32 e_ = lds16(s_tab + (((hi) >> sh) << 1));                     \
+            const u32 i_ = (hi) >> sh;                                             \
+            const u32 e_ = lds16(L1BITS >= KZG_HUF_MAXBITS ? s_l1 + (i_ << 1) : (i_ < nlong ? s_l2 + (i_ << 1) : s_l1 + ((i_ >> sshift) << 1))); \
             const u32 l_ = e_ >> 8;                                                \
             sym = e_ & 255u;                                                       \
             hi = __funnelshift_l(lo, hi, l_);                                      \
@@ -205,8 +230,9 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
     }
 }
 
+template <u32 L1BITS, u32 L2CAP, bool SECOND>
 __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B) {
     extern __shared__ uint4 smem4[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    kzg_huf_warp_loop(B, reinterpret_cast<u8*>(smem4) + warp * KZG_HUF_WARP_SMEM, lane, nullptr, 0);
+    kzg_huf_warp_loop<L1BITS, L2CAP, SECOND>(B, reinterpret_cast<u8*>(smem4) + warp * KZG_HUF_WARP_SMEM_OF(L1BITS, L2CAP), lane, nullptr, 0);
 }

@@ -159,7 +159,7 @@ KZG_HD void kzg_stage_link(const KzgBatch& B, u32 i) {
 }
 
 // huffman: decode stream `st` of Huffman block h (index into hlist) with the already built table
-KZG_HD void kzg_stage_huf_stream(const KzgBatch& B, KzgCBlock* cb, u32 st, const u16* tab, u32 maxbits) {
+KZG_HD void kzg_stage_huf_stream(const KzgBatch& B, KzgCBlock* cb, u32 st, const u16* l1, const u16* l2, u32 nlong, u32 maxbits) {
     const u32 regen = cb->lit_regen;
     const u8* src = B.src + cb->src + cb->lit_src;
     u8* dst = B.lit_pool + cb->lit_out;
@@ -171,7 +171,7 @@ KZG_HD void kzg_stage_huf_stream(const KzgBatch& B, KzgCBlock* cb, u32 st, const
         dst += st * seg;
         cnt = st < 3 ? seg : regen - 3 * seg;
     }
-    const u32 e = kzg_huf_decode_stream(src, size, tab, maxbits, dst, cnt);
+    const u32 e = kzg_huf_decode_stream(src, size, l1, l2, nlong, maxbits, dst, cnt);
     if (e) cb->status_lit = e;
 }
 

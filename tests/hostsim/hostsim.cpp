@@ -35,6 +35,8 @@ static u64 xxh64(const u8* p, u64 len) {
 
 // Execute step: 0 = sequential stand-in, 1 / 2 = kzg_exec2_block on the warp emulator (lanes scheduled in forward /
 // reverse order), with the ring size TILE.  What kzg_bulk_kernel does is done sequentially first, as on the GPU.
+static u64 g_huf_long_max = 0, g_huf_long_sum = 0, g_huf_tables = 0;      // statistics of the two-level Huffman tables
+extern "C" void kzs_huf_stats(u64* out) { out[0] = g_huf_long_max; out[1] = g_huf_long_sum; out[2] = g_huf_tables; g_huf_long_max = g_huf_long_sum = g_huf_tables = 0; }
 static int g_exec_mode = 0;
 static u32 g_exec_tile = 8192;
 static u64 g_exec_deferred = 0, g_exec_collectives = 0;
@@ -64,6 +66,7 @@ static u32 x2_run_frame(const KzgBatch& B, u32 f) {
     switch (g_exec_tile) {
         case 4096: simt::run_warp(x2_lane<4096>, &A, KzgX2<4096>::BYTES, rev); break;
         case 16384: simt::run_warp(x2_lane<16384>, &A, KzgX2<16384>::BYTES, rev); break;
+        case 32768: simt::run_warp(x2_lane<32768>, &A, KzgX2<32768>::BYTES, rev); break;
         default: simt::run_warp(x2_lane<8192>, &A, KzgX2<8192>::BYTES, rev); break;
     }
     return A.result;
@@ -107,17 +110,23 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     if (ctr.overflow) return -1;
     for (u32 c = 0; c < ctr.n_cblocks; c++) kzg_stage_parse(B, c);
     for (u32 i = 0; i < n; i++) kzg_stage_link(B, i);
-    // huffman: 4 "lanes" per block build the table, then each stream decodes
-    std::vector<u16> tab(1u << KZG_HUF_MAXBITS);
+    // huffman: 4 "lanes" per block build the two-level table, then each stream decodes
+    alignas(16) static u16 l1[1u << KZG_HUF_L1_BITS];
+    alignas(16) static u16 l2[1u << KZG_HUF_MAXBITS];
     for (u32 h = 0; h < ctr.n_hblocks; h++) {
         KzgCBlock* cb = &cblocks[hlist[h]];
         if (cb->status_lit != KZG_OK || cb->huf_owner == KZG_INVALID_OWNER) continue;
         const KzgHufDesc* hd = kzg_huf_desc_of(B, cb->huf_owner);
         alignas(16) KzgHufScratch sc;
+        for (u32 k = 0; k < (1u << KZG_HUF_L1_BITS); k++) l1[k] = 0xDEAD;
+        for (u32 k = 0; k < (1u << KZG_HUF_MAXBITS); k++) l2[k] = 0xDEAD;
         for (u32 st = 0; st < 4; st++) kzg_huf_build_phase1(&sc, hd->weight, hd->nsym, st);
+        const u32 nlong = kzg_huf_long_entries(&sc, hd->maxbits);
+        if (nlong > g_huf_long_max) g_huf_long_max = nlong;
+        g_huf_long_sum += nlong; g_huf_tables++;
         for (u32 st = 0; st < 4; st++) kzg_huf_build_phase2(&sc, hd->maxbits, st);
-        for (u32 st = 0; st < 4; st++) kzg_huf_build_phase3(tab.data(), &sc, hd->nsym, hd->maxbits, st);
-        for (u32 st = 0; st < cb->n_streams; st++) kzg_stage_huf_stream(B, cb, st, tab.data(), hd->maxbits);
+        for (u32 st = 0; st < 4; st++) kzg_huf_build_phase3(l1, l2, &sc, hd->nsym, hd->maxbits, st);
+        for (u32 st = 0; st < cb->n_streams; st++) kzg_stage_huf_stream(B, cb, st, l1, l2, nlong, hd->maxbits);
     }
     alignas(16) static u16 t3[1280];
     alignas(16) static u16 scrLL[40];
