@@ -144,8 +144,10 @@ struct KzgCounters {
     u32 n_defer;            // entries of dlist
     u32 ticket_exec2;
     u32 n_hblocks2, ticket_huf2;   // Huffman blocks whose table does not fit the compact two-level layout (second launch)
+    u32 ticket_exec4;              // the CTA-per-frame execute kernel's ticket over dlist
 };
 
+#define KZG_DEFER_BIG 0x80000000u
 #define KZG_INVALID_OWNER 0xFFFFFFFEu
 #define KZG_DICT_OWNER 0xFFFFFFFDu      // table comes from the formatted dictionary loaded into the context
 
@@ -161,6 +163,7 @@ struct KzgBatch {
     u64* out_size;      // out: decoded bytes per frame
     u32 n_frames;
     u32 tile_bytes;     // shared-memory output tile of the execute kernel (>= largest block)
+    u32 big_by_cta;     // frames of many blocks are left to the CTA-per-frame execute kernel (set at launch)
     // workspace
     KzgFrame* frames;
     KzgBlock* blocks;
@@ -171,7 +174,7 @@ struct KzgBatch {
     u32* hlist2;        // ... of those, the ones left to the second Huffman launch (worst-case table layout)
     u32* slist;         // compressed blocks with sequences
     u32* blist;         // blocks with work for the bulk kernel (filled by the offsets stage)
-    u32* dlist;         // frames the hot execute kernel left to the full one (long runs)
+    u32* dlist;         // frames the hot execute kernel left to the others: long runs (full variant); KZG_DEFER_BIG set: many blocks (CTA per frame)
     u8* lit_pool;
     u64* seq_pool;
     u16* fse_tab;       // built FSE decode tables, 1280 cells (LL 512 | ML 512 | OF 256) per entry of slist

@@ -541,7 +541,10 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch
         if (lane == 0) f = atomicAdd(FULL ? &B.ctr->ticket_exec2 : &B.ctr->ticket_exec, 1u);
         f = __shfl_sync(0xFFFFFFFFu, f, 0);
         if (f >= (FULL ? B.ctr->n_defer : B.n_frames)) break;
-        if (FULL) f = B.dlist[f];
+        if (FULL) {
+            f = B.dlist[f];
+            if (f & KZG_DEFER_BIG) continue;            // a frame of many blocks: kzg_exec4_kernel's
+        }
         const KzgFrame* fr = &B.frames[f];
         if (fr->status != KZG_OK) continue;
         u8* const fdst = B.dst + B.dst_off[f];
@@ -566,6 +569,7 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch
             __syncwarp();
         }
         if (failed && lane == 0) B.frames[f].status = KZG_E_CORRUPTION;
-        if (deferred && lane == 0) B.dlist[atomicAdd(&B.ctr->n_defer, 1u)] = f;      // the full kernel redoes this frame
+        // the full variant redoes a frame with long runs; a frame of many blocks goes to the CTA-per-frame kernel
+        if (deferred && lane == 0) B.dlist[atomicAdd(&B.ctr->n_defer, 1u)] = f | ((B.big_by_cta && nblk > KZG_EX_BIG_FRAME_BLOCKS) ? KZG_DEFER_BIG : 0u);
     }
 }

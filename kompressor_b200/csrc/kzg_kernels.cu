@@ -24,6 +24,8 @@
 #include "kzg_bulk.cuh"
 #include "kzg_exec.cuh"
 #include "kzg_exec2.cuh"
+#include "kzg_exec3.cuh"
+#include "kzg_exec4.cuh"
 #include <stdlib.h>
 #include <mutex>
 
@@ -156,9 +158,11 @@ const char* const kzg_stage_names[KZG_N_STAGES] = { "scan", "parse", "link", "fs
 // every launch so that one process can compare them.
 struct KzgExecChoice { int design; u32 tile; };
 static KzgExecChoice kzg_exec_choice() {
-    KzgExecChoice r{ 1, 8192u };
-    if (const char* e = getenv("KZG_EXEC")) r.design = atoi(e) == 2 ? 2 : 1;
-    if (const char* e = getenv("KZG_EXEC_TILE")) { const u32 t = (u32)strtoul(e, nullptr, 10); if (t == 4096u || t == 8192u) r.tile = t; }
+    KzgExecChoice r{ 1, 0u };
+    if (const char* e = getenv("KZG_EXEC")) { const int d = atoi(e); r.design = d >= 1 && d <= 4 ? d : 1; }
+    if (const char* e = getenv("KZG_EXEC_TILE")) r.tile = (u32)strtoul(e, nullptr, 10);
+    if (r.design == 2 && r.tile != 4096u) r.tile = 8192u;
+    if (r.design == 3 && r.tile != 512u && r.tile != 2048u) r.tile = 1024u;
     return r;
 }
 
@@ -177,12 +181,18 @@ int kzg_kernels_init_device(int device) {
     opt((const void*)kzg_exec_kernel<true>, KZG_EX_SMEM);
     opt((const void*)kzg_exec2_kernel<4096>, KZG_X2_WARPS * KzgX2<4096>::BYTES);
     opt((const void*)kzg_exec2_kernel<8192>, KZG_X2_WARPS * KzgX2<8192>::BYTES);
+    opt((const void*)kzg_exec4_kernel<false>, KZG_X4_SMEM);
+    opt((const void*)kzg_exec4_kernel<true>, KZG_X4_SMEM);
+    opt((const void*)kzg_exec3_kernel<512>, KzgX3<512>::BYTES);
+    opt((const void*)kzg_exec3_kernel<1024>, KzgX3<1024>::BYTES);
+    opt((const void*)kzg_exec3_kernel<2048>, KzgX3<2048>::BYTES);
     if (e != cudaSuccess) { cudaGetLastError(); return -1; }
     if (device >= 0 && device < 256) done_mask[device >> 6] |= 1ull << (device & 63);
     return 0;
 }
 
-int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
+int kzg_launch_batch(const KzgBatch& b_in, int sm_count, cudaStream_t stream, cudaEvent_t* ev) {
+    KzgBatch b = b_in;
     const size_t huf_smem = KZG_HUF_SMEM;
     // literal warps riding along in the sequence kernel (KZG_FSE_LITWARPS, 0..3: development knob, read at every launch)
     u32 nlit = KZG_FSE_LIT_WARPS_MAX;
@@ -218,9 +228,26 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
     kzg_bulk_kernel<<<sm_count * 4, KZG_BULK_THREADS, 0, stream>>>(b);
     KZG_MARK();
     const int exec_per_sm = (int)((227 * 1024) / (exec_smem + 1024));
-    const KzgExecChoice ch = kzg_exec_choice();
-    if (ch.design == 1) kzg_exec_kernel<false><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
-    else {
+    KzgExecChoice ch = kzg_exec_choice();
+    if (ch.design == 3 && b.dict_size) ch.design = 1;          // history before the frame: the first design reads it
+    // Few frames cannot fill the GPU one warp each: below this many, every frame gets a CTA (kzg_exec4.cuh).
+    u32 cta_all_below = (u32)sm_count * 2u;
+    if (const char* e = getenv("KZG_EXEC_CTA_BELOW")) cta_all_below = (u32)strtoul(e, nullptr, 10);
+    if (ch.design == 1 && n < cta_all_below) ch.design = 4;
+    bool big_by_cta = true;                                     // deferred frames: the CTA kernel (0: the first design's full variant)
+    if (const char* e = getenv("KZG_EXEC_BIG")) big_by_cta = atoi(e) != 0;
+    b.big_by_cta = big_by_cta ? 1u : 0u;
+    if (ch.design == 4) kzg_exec4_kernel<true><<<min((u32)sm_count, n), KZG_X4_THREADS, KZG_X4_SMEM, stream>>>(b);
+    else if (ch.design == 1) kzg_exec_kernel<false><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
+    else if (ch.design == 3) {
+        // a thread per frame: one warp per CTA, as many CTAs per SM as the rings allow
+#define KZG_X3_LAUNCH(T) do { const size_t sm_ = KzgX3<T>::BYTES; const int per_sm_ = (int)((228 * 1024) / (sm_ + 1024)); \
+        kzg_exec3_kernel<T><<<sm_count * per_sm_, 32, sm_, stream>>>(b); } while (0)
+        if (ch.tile == 512u) KZG_X3_LAUNCH(512);
+        else if (ch.tile == 2048u) KZG_X3_LAUNCH(2048);
+        else KZG_X3_LAUNCH(1024);
+#undef KZG_X3_LAUNCH
+    } else {
         // one warp per frame, KZG_X2_WARPS per CTA, as many CTAs per SM as the ring size allows
 #define KZG_X2_LAUNCH(T) do { const size_t sm_ = KZG_X2_WARPS * KzgX2<T>::BYTES; const int per_sm_ = (int)((228 * 1024) / (sm_ + 1024)); \
         kzg_exec2_kernel<T><<<sm_count * (per_sm_ > 16 ? 16 : per_sm_), KZG_X2_WARPS * 32, sm_, stream>>>(b); } while (0)
@@ -231,10 +258,16 @@ int kzg_launch_batch(const KzgBatch& b, int sm_count, cudaStream_t stream, cudaE
 #undef KZG_X2_LAUNCH
     }
     KZG_MARK();
-    kzg_exec_kernel<true><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);     // deferred frames only
+    // deferred frames only: long runs -> the first design's full variant; many blocks -> a CTA per frame
+    int launched = KZG_N_STAGES + 1;                            // the Huffman stage is two launches
+    if (ch.design == 4) launched--;                             // nothing was deferred: one launch fewer
+    else {
+        kzg_exec_kernel<true><<<sm_count * exec_per_sm, KZG_EX_WARPS * 32, exec_smem, stream>>>(b);
+        if (big_by_cta) { kzg_exec4_kernel<false><<<sm_count, KZG_X4_THREADS, KZG_X4_SMEM, stream>>>(b); launched++; }
+    }
     KZG_MARK();
     kzg_finish_kernel<<<(n * 4 + 127) / 128, 128, 0, stream>>>(b);
     KZG_MARK();
 #undef KZG_MARK
-    return KZG_N_STAGES + 1;        // kernels launched (the Huffman stage is two launches)
+    return launched;                // kernels launched
 }

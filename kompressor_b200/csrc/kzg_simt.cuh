@@ -20,8 +20,10 @@ __device__ __forceinline__ u32 w_shfl(u32 v, u32 src) { return __shfl_sync(KZG_F
 __device__ __forceinline__ u32 w_shfl_up(u32 v, u32 d) { return __shfl_up_sync(KZG_FULL, v, d); }
 __device__ __forceinline__ u32 w_ballot(bool p) { return __ballot_sync(KZG_FULL, p); }
 __device__ __forceinline__ bool w_any(bool p) { return __any_sync(KZG_FULL, p); }
+__device__ __forceinline__ u32 w_or(u32 v) { return __reduce_or_sync(KZG_FULL, v); }          // REDUX: OR over the warp
 __device__ __forceinline__ void w_sync() { __syncwarp(); }
 __device__ __forceinline__ void fence_block() { __threadfence_block(); }
+__device__ __forceinline__ void fence_gpu() { __threadfence(); }
 
 __device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
@@ -73,8 +75,12 @@ __device__ __forceinline__ u32 ldg8_ro(const u8* p) { return (u32)__ldg(p); }
 __device__ __forceinline__ u32 ldg32_ro(const u32* p) { return __ldg(p); }
 __device__ __forceinline__ u64 ldg64_stream(const u64* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg8(u8* p, u32 v) { *p = (u8)v; }
+__device__ __forceinline__ void stg128(u8* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ u64 ldg64_ro(const u64* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ u32 atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
 
 __device__ __forceinline__ u32 funnel_r(u32 lo, u32 hi, u32 sh) { return __funnelshift_r(lo, hi, sh); }
+__device__ __forceinline__ u32 funnel_l(u32 lo, u32 hi, u32 sh) { return __funnelshift_l(lo, hi, sh); }   // high word of (hi:lo) << (sh & 31)
 __device__ __forceinline__ u32 shl_clamp(u32 v, u32 n) { u32 r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }   // n >= 32 -> 0
 __device__ __forceinline__ u32 shr_clamp(u32 v, u32 n) { u32 r; asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 __device__ __forceinline__ u32 clz32(u32 v) { return (u32)__clz((int)v); }

@@ -7,6 +7,7 @@
 #define KZG_SIMT_EMU 1
 #include "../../kompressor_b200/csrc/kzg_stages.cuh"
 #include "../../kompressor_b200/csrc/kzg_exec2.cuh"      // the second execute design, run on the lock-step warp emulator (simt_emu.h)
+#include "../../kompressor_b200/csrc/kzg_exec3.cuh"      // the third one (a thread per frame), likewise
 
 #include <stdlib.h>
 #include <string.h>
@@ -72,6 +73,44 @@ static u32 x2_run_frame(const KzgBatch& B, u32 f) {
     return A.result;
 }
 
+// Execute modes 3 / 4 (5 / 6: with eager asynchronous copies): kzg_exec3_warp (lanes in forward / reverse order), ring size g_exec_tile; one emulated warp takes
+// all frames of the batch by ticket.
+struct X3Arg { const KzgBatch* B; };
+template <u32 W> static void x3_lane(void* p, u32 lane) { kzg_exec3_warp<W>(*((X3Arg*)p)->B, simt::Warp::SMEM_BASE, lane); }
+static void x3_run_batch(const KzgBatch& B) {
+    X3Arg A{ &B };
+    const bool rev = g_exec_mode == 4 || g_exec_mode == 6;
+    simt::g_cp_eager = g_exec_mode >= 5;           // modes 5 / 6: asynchronous copies land at once (early-overwrite mistakes show)
+    switch (g_exec_tile) {
+        case 512: simt::run_warp(x3_lane<512>, &A, KzgX3<512>::BYTES, rev); break;
+        case 2048: simt::run_warp(x3_lane<2048>, &A, KzgX3<2048>::BYTES, rev); break;
+        default: simt::run_warp(x3_lane<1024>, &A, KzgX3<1024>::BYTES, rev); break;
+    }
+}
+
+// What kzg_bulk_kernel writes for frame fr (kzg_bulk.cuh); with_runs: also the long literal runs of flagged blocks.
+static void bulk_standin(const KzgBatch& B, const KzgFrame& fr, u8* fdst, bool with_runs) {
+    for (u32 k = 0; k < fr.n_blocks; k++) {
+        const KzgBlock& blk = B.blocks[fr.first_block + k];
+        u8* out = fdst + blk.out_off;
+        if (blk.type == 0) { memcpy(out, B.src + blk.src, blk.regen); continue; }
+        if (blk.type == 1) { memset(out, B.src[blk.src], blk.regen); continue; }
+        const KzgCBlock& cb = B.cblocks[blk.cidx];
+        const u8* l = cb.lit_type >= 2 ? B.lit_pool + cb.lit_out : B.src + cb.src + cb.lit_src;
+        if (cb.n_seq == 0) { if (cb.lit_type == 1) memset(out, l[0], blk.regen); else memcpy(out, l, blk.regen); continue; }
+        const u32 trail = cb.lit_regen - cb.lit_used;
+        if (trail >= KZG_BULK_MIN) { if (cb.lit_type == 1) memset(out + blk.regen - trail, l[0], trail); else memcpy(out + blk.regen - trail, l + cb.lit_used, trail); }
+        if (!with_runs || !cb.bulk_lits) continue;
+        u32 p_lit = 0, p_out = 0;
+        for (u32 q = 0; q < cb.n_seq; q++) {
+            const u64 rec = B.seq_pool[cb.seq_out + q];
+            const u32 lit_end = (u32)(rec >> 28) & 0x3FFFF, ll = lit_end - p_lit;
+            if (lit_end >= p_lit && ll >= KZG_BULK_MIN && p_out + ll <= blk.regen) { if (cb.lit_type == 1) memset(out + p_out, l[0], ll); else memcpy(out + p_out, l + p_lit, ll); }
+            p_lit = lit_end; p_out = (u32)(rec >> 46);
+        }
+    }
+}
+
 extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* src_off, const u64* src_size, u64 n,
                                     u8* dst, const u64* dst_off, const u64* dst_cap, u32* status, u64* out_size,
                                     u64* seq_dump, u64 seq_dump_cap, u8* lit_dump, u64 lit_dump_cap) {
@@ -88,7 +127,7 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     std::vector<KzgCBlock> cblocks(block_cap);
     std::vector<KzgFseDesc> fse(block_cap);
     std::vector<KzgHufDesc> huf(block_cap);
-    std::vector<u32> hlist(block_cap), slist(block_cap), blist(block_cap);
+    std::vector<u32> hlist(block_cap), slist(block_cap), blist(block_cap), dlist(n + 1);
     std::vector<u8> lit(total_dst + 64 * block_cap + 4096 + 16);
     std::vector<u64> seq(total_dst / 3 + 4096);
     KzgCounters ctr;
@@ -102,7 +141,7 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     B.src = src; B.src_off = src_off; B.src_size = src_size; B.dst = dst; B.dst_off = dst_off; B.dst_cap = dst_cap;
     B.status = status; B.out_size = out_size; B.n_frames = (u32)n; B.tile_bytes = KZG_BLOCK_MAX + 64;
     B.frames = frames.data(); B.blocks = blocks.data(); B.cblocks = cblocks.data(); B.fse = fse.data(); B.huf = huf.data();
-    B.hlist = hlist.data(); B.slist = slist.data(); B.blist = blist.data();
+    B.hlist = hlist.data(); B.slist = slist.data(); B.blist = blist.data(); B.dlist = dlist.data();
     B.lit_pool = (u8*)(((uintptr_t)lit.data() + 15) & ~(uintptr_t)15); B.seq_pool = seq.data(); B.ctr = &ctr;
     B.fse_default = &def; B.code_tables = codes; B.lit_cap = lit.size() - 32; B.seq_cap = seq.size();
     B.block_cap = (u32)block_cap; B.cblock_cap = (u32)block_cap;
@@ -137,13 +176,20 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
     // optional dumps (first compressed block order) for stage-by-stage comparison
     if (seq_dump) { u64 m = ctr.seq_used < seq_dump_cap ? ctr.seq_used : seq_dump_cap; memcpy(seq_dump, seq.data(), m * 8); }
     if (lit_dump) { u64 m = ctr.lit_used < lit_dump_cap ? ctr.lit_used : lit_dump_cap; memcpy(lit_dump, B.lit_pool, m); }
+    const bool x3 = g_exec_mode >= 3 && g_exec_mode <= 6;
+    if (x3) {
+        for (u32 f = 0; f < n; f++) if (!frames[f].status) bulk_standin(B, frames[f], dst + dst_off[f], true);
+        ctr.ticket_exec = 0; ctr.n_defer = 0;
+        x3_run_batch(B);
+        g_exec_deferred += ctr.n_defer;
+    }
     // sequential execute + finish
     for (u32 f = 0; f < n; f++) {
         KzgFrame& fr = frames[f];
         u32 st = fr.status;
         u8* fdst = dst + dst_off[f];
-        bool emulated = false;
-        if (g_exec_mode != 0 && !st) {
+        bool emulated = x3;
+        if (g_exec_mode != 0 && !x3 && !st) {
             // what kzg_bulk_kernel writes (kzg_bulk.cuh), then the warp-emulated execute kernel
             for (u32 k = 0; k < fr.n_blocks; k++) {
                 const KzgBlock& blk = blocks[fr.first_block + k];

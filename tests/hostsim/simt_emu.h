@@ -21,7 +21,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 namespace simt {
 
-enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_ANY, OP_SYNC, OP_DONE };
+enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_ANY, OP_SYNC, OP_OR, OP_DONE };
 
 struct PendingCp { uint32_t group; uint32_t dst; const uint8_t* src; };
 struct PendingBulk { uint32_t group; uint8_t* g; uint32_t s; uint32_t n; std::vector<uint8_t> snap; };
@@ -48,6 +48,7 @@ struct Warp {
 };
 
 static thread_local Warp* g_w = nullptr;
+static bool g_cp_eager = false;        // cp.async copies land at once instead of as late as their wait allows
 
 [[noreturn]] static inline void die(const char* msg, int site = 0) {
     fprintf(stderr, "simt_emu: %s (site %d, lane %d)\n", msg, site, g_w ? g_w->cur : -1);
@@ -100,14 +101,15 @@ static inline void run_warp(void (*fn)(void*, uint32_t), void* arg, size_t smem_
             }
         if (op == OP_DONE) break;
         w.n_collectives++;
-        uint32_t mask = 0;
-        for (int l = 0; l < Warp::W; l++) if (w.a0[l]) mask |= 1u << l;
+        uint32_t mask = 0, orv = 0;
+        for (int l = 0; l < Warp::W; l++) { if (w.a0[l]) mask |= 1u << l; orv |= w.a0[l]; }
         for (int l = 0; l < Warp::W; l++) {
             switch (op) {
                 case OP_SHFL: w.res[l] = w.a0[w.a1[l] & 31u]; break;
                 case OP_SHFL_UP: w.res[l] = (uint32_t)l >= w.a1[l] ? w.a0[l - w.a1[l]] : w.a0[l]; break;
                 case OP_BALLOT: w.res[l] = mask; break;
                 case OP_ANY: w.res[l] = mask != 0; break;
+                case OP_OR: w.res[l] = orv; break;
                 default: w.res[l] = 0; break;
             }
         }
@@ -125,7 +127,9 @@ static inline uint32_t w_shfl_up(uint32_t v, uint32_t d, int site = KZG_SITE) { 
 static inline uint32_t w_ballot(bool p, int site = KZG_SITE) { return collective(OP_BALLOT, site, p ? 1u : 0u, 0); }
 static inline bool w_any(bool p, int site = KZG_SITE) { return collective(OP_ANY, site, p ? 1u : 0u, 0) != 0; }
 static inline void w_sync(int site = KZG_SITE) { collective(OP_SYNC, site, 0, 0); }
+static inline uint32_t w_or(uint32_t v, int site = KZG_SITE) { return collective(OP_OR, site, v, 0); }
 static inline void fence_block() {}
+static inline void fence_gpu() {}
 
 static inline uint8_t* sm(uint32_t a, uint32_t n, uint32_t align) {
     Warp* w = g_w;
@@ -149,6 +153,7 @@ static inline void cp_async16_if(bool p, uint32_t dst, const void* src) {
     Warp* w = g_w;
     sm(dst, 16, 16);
     if ((uintptr_t)src & 15) die("misaligned cp.async source");
+    if (g_cp_eager) { memcpy(sm(dst, 16, 16), src, 16); return; }
     w->cp[w->cur].push_back(PendingCp{ w->cp_group[w->cur], dst, (const uint8_t*)src });
 }
 static inline void cp_commit() { g_w->cp_group[g_w->cur]++; }
@@ -197,8 +202,12 @@ static inline uint32_t ldg8_ro(const uint8_t* p) { return *p; }
 static inline uint32_t ldg32_ro(const uint32_t* p) { return *p; }
 static inline uint64_t ldg64_stream(const uint64_t* p) { return *p; }
 static inline void stg8(uint8_t* p, uint32_t v) { *p = (uint8_t)v; }
+static inline void stg128(uint8_t* p, uint4 v) { if ((uintptr_t)p & 15) die("misaligned 16-byte global store"); memcpy(p, &v, 16); }
+static inline uint64_t ldg64_ro(const uint64_t* p) { return *p; }
+static inline uint32_t atomic_add(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
 
 static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31u; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+static inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31u; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline uint32_t shl_clamp(uint32_t v, uint32_t n) { return n >= 32 ? 0u : v << n; }
 static inline uint32_t shr_clamp(uint32_t v, uint32_t n) { return n >= 32 ? 0u : v >> n; }
 static inline uint32_t clz32(uint32_t v) { return v ? (uint32_t)__builtin_clz(v) : 32u; }

@@ -204,7 +204,7 @@ def test_device_resident_batch_and_size_independent_properties(dec):
     h_exp = hashlib.sha256(b"".join(hashlib.sha256(r.tobytes()).digest() for r in exp)).hexdigest()
     assert h_got == h_exp
     st = dec.stats()
-    assert st.n_cblocks == n and st.launches == 12      # ten stages, the Huffman stage is two launches
+    assert st.n_cblocks == n and st.launches in (11, 13)      # the Huffman stage is two launches, the execute stage one or three
 
 
 def test_hostile_content_size_does_not_reach_the_allocator(dec, libzstd):
