@@ -76,6 +76,7 @@ struct KzgFrame {           // one per input frame
     u32 status;             // frame-level error found by the scan
     u32 block_max;
     u32 xxh_lo;             // low 32 bits of XXH64 computed by the checksum kernel
+    u32 lit_garbage;        // a block's Huffman stream ran out of bits where libzstd's fast loops make up literals (see kzg_huf_verdict)
 };
 
 struct KzgBlock {           // one per block of every frame
@@ -118,6 +119,7 @@ struct KzgCBlock {          // one per compressed block
     u32 rep_final[3];       // encoded (possibly symbolic) repeat offsets after the block
     u32 first_in_frame;     // 1 if no compressed block with sequences precedes it in its frame
     u32 bulk_lits;          // 1 if the literal runs of >= KZG_BULK_MIN bytes add up to >= KZG_BULK_SUM: the bulk kernel copies them
+    u32 lit_garbage;        // a Huffman stream ran out of bits in a block libzstd decodes with its fast loops
 };
 
 struct KzgFseDesc {         // entropy description parsed from a compressed block

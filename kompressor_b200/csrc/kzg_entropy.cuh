@@ -189,7 +189,22 @@ KZG_HD u32 kzg_huf_decode_stream(const u8* src, u32 size, const u16* l1, const u
         dst[i++] = (u8)s;
     }
 #undef KZG_HUF_SYM
-    return b.left == 0 ? KZG_OK : KZG_E_CORRUPTION;
+    return b.left == 0 ? 0u : (b.left > 0 ? 1u : 2u);       // exactly consumed / bits left over / ran out of bits
+}
+
+// What a Huffman stream that was not consumed exactly means.  RFC 8878 4.2.2 wants every stream consumed exactly, and
+// libzstd 1.5.7 checks that in its plain loops (one stream, or four streams one of which is shorter than 8 bytes).  Its
+// fast four-stream loops (HUF_decompress4X*_usingDTable_internal_fast) only verify the symbol count: left-over bits are
+// accepted (same bytes here), and a stream that runs out of bits yields literals made up from a stale bit container,
+// which this decoder does not reproduce -- the block is flagged and its frame ends as checksum_wrong when it carries a
+// checksum (libzstd's verdict, a 2^-32 chance aside) and as corruption_detected when it does not.
+//   ends: 0 exact, 1 bits left over, 2 ran out of bits.  Returns true if the block is corrupt; may set cb->lit_garbage.
+KZG_HD bool kzg_huf_verdict(KzgCBlock* cb, u32 ends) {
+    if (ends == 0) return false;
+    const u32 m = cb->n_streams == 4 ? (cb->stream_size[0] < 8u || cb->stream_size[1] < 8u || cb->stream_size[2] < 8u || cb->stream_size[3] < 8u) : 1u;
+    if (m) return true;
+    if (ends == 2) cb->lit_garbage = 1u;
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -84,11 +84,16 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
     // misc[0..15]: completed lanes of every warp; misc[32], misc[33]: literal range of the step; misc[34]: its first output
     volatile u32* oend = reinterpret_cast<volatile u32*>(__cvta_shared_to_generic(smem + KZG_X4_WIN + KZG_X4_LIT_BYTES + KZG_X4_MISC + KZG_X4_THREADS * KZG_X4_MSTAGE));
 
+    u64 rec_n = tid < nseq ? __ldg(seqs + tid) : 0ull, prev_n = (tid && tid < nseq) ? __ldg(seqs + tid - 1) : 0ull;         // the step's records are fetched one step ahead
     for (u32 sb0 = 0; sb0 < nseq; sb0 += KZG_X4_THREADS) {
         const u32 i = sb0 + tid;
         const bool valid = i < nseq;
-        const u64 rec = valid ? __ldg(seqs + i) : 0ull;
-        const u64 prev = (valid && i) ? __ldg(seqs + i - 1) : 0ull;
+        const u64 rec = rec_n, prev = prev_n;
+        {
+            const u32 in = i + KZG_X4_THREADS;
+            rec_n = in < nseq ? __ldg(seqs + in) : 0ull;
+            prev_n = in < nseq ? __ldg(seqs + in - 1) : 0ull;
+        }
         const u32 lit_end = (u32)(rec >> 28) & 0x3FFFFu, p_lit_end = (u32)(prev >> 28) & 0x3FFFFu;
         const u32 out_end = (u32)(rec >> 46), p_out_end = (u32)(prev >> 46);
         const u32 ll = valid ? lit_end - p_lit_end : 0u;
@@ -241,6 +246,7 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
             }
             if (nowdone == 0xFFFFFFFFu) break;
             if (++trips > (1u << 22)) { if (lane == 0) misc[35] = 1u; break; }      // cannot happen; never spin forever on a GPU
+            if (!gm) __nanosleep(40);           // nothing went: this warp only polls, leave the issue slots to the others
             go = false;
             if (pending) {
                 bool ok = true;

@@ -225,7 +225,8 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
 #undef KZG_HUF_SERVICE
 #undef KZG_HUF_WINDOW
         cp_wait<0>();
-        if (mine && (bad || P != lowbits)) cb->status_lit = KZG_E_CORRUPTION;     // every stream must be consumed exactly
+        // a stream that is not consumed exactly: corrupt, or (libzstd's fast loops) accepted / flagged -- kzg_huf_verdict
+        if (mine && (bad || kzg_huf_verdict(cb, P == lowbits ? 0u : (P > lowbits ? 1u : 2u)))) cb->status_lit = KZG_E_CORRUPTION;
         __syncwarp();
     }
 }

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
         fr = &B.frames[f];
         status = (B.ctr->overflow & 3u) ? (u32)KZG_E_INTERNAL_OVERFLOW : fr->status;
         len = fr->out_size;
+        // literals libzstd would have made up (kzg_huf_verdict): its checksum cannot match; without one the frame is rejected
+        if (status == KZG_OK && fr->lit_garbage) status = fr->checksum_off != KZG_NONE ? (u32)KZG_E_CHECKSUM_WRONG : (u32)KZG_E_CORRUPTION;
         do_sum = status == KZG_OK && fr->checksum_off != KZG_NONE;
     }
     u64 acc = 0;

@@ -33,7 +33,7 @@ KZG_HD void kzg_stage_scan(const KzgBatch& B, u32 i) {
     const u64 fsz = B.src_size[i];
     KzgFrame fr;
     fr.window_size = 0; fr.fcs = ~0ull; fr.out_size = 0; fr.first_block = 0; fr.n_blocks = 0;
-    fr.hdr_size = 0; fr.dict_id = 0; fr.checksum_off = KZG_NONE; fr.status = KZG_OK; fr.block_max = 0; fr.xxh_lo = 0;
+    fr.hdr_size = 0; fr.dict_id = 0; fr.checksum_off = KZG_NONE; fr.status = KZG_OK; fr.block_max = 0; fr.xxh_lo = 0; fr.lit_garbage = 0;
     if (fsz >= 8 && (kzg_rd32(f) & 0xFFFFFFF0u) == KZG_SKIP_MAGIC) {     // skippable frame: no output
         if (8ull + kzg_rd32(f + 4) != fsz) fr.status = KZG_E_SRCSIZE_WRONG;
         B.frames[i] = fr;
@@ -109,6 +109,7 @@ KZG_HD void kzg_stage_parse(const KzgBatch& B, u32 c) {
     cb.rep_final[0] = 1; cb.rep_final[1] = 4; cb.rep_final[2] = 8;
     cb.first_in_frame = 0;
     cb.bulk_lits = 0;
+    cb.lit_garbage = 0;
     if (cb.status_lit == KZG_OK && cb.lit_type >= 2) {
         const u64 sz = ((u64)cb.lit_regen + 31) & ~15ull;
         const u64 off = KZG_ATOMIC_ADD64(&B.ctr->lit_used, sz);
@@ -172,7 +173,7 @@ KZG_HD void kzg_stage_huf_stream(const KzgBatch& B, KzgCBlock* cb, u32 st, const
         cnt = st < 3 ? seg : regen - 3 * seg;
     }
     const u32 e = kzg_huf_decode_stream(src, size, l1, l2, nlong, maxbits, dst, cnt);
-    if (e) cb->status_lit = e;
+    if (e == KZG_E_CORRUPTION || kzg_huf_verdict(cb, e)) cb->status_lit = KZG_E_CORRUPTION;
 }
 
 // fse: build the three tables of block cb into tLL/tML/tOF and run the sequence state machine
@@ -221,6 +222,7 @@ KZG_HD void kzg_stage_offsets(const KzgBatch& B, u32 i) {
             KzgCBlock* cb = &B.cblocks[blk->cidx];
             err = cb->status_lit ? cb->status_lit : cb->status_seq;
             if (err) break;
+            if (cb->lit_garbage) fr->lit_garbage = 1u;
             u32 regen = cb->lit_regen;
             if (cb->n_seq > 0) {
                 regen = cb->regen;

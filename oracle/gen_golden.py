@@ -107,6 +107,44 @@ def main() -> None:
     add_err("err_needs_dictionary", fr, "frame needs the dictionary, none loaded -> -20")
     add_err("err_reserved_bit", bytes.fromhex("28b52ffd") + bytes([0x28, 1]) + bytes([0x09, 0x00, 0x00, 0x41]), "reserved header bit -> -14")
 
+    # --- Huffman streams that are not consumed exactly.  Single-bit flips inside the literal streams of
+    # one frame, found by a seeded search; libzstd's verdict is recorded, and for the one documented divergence also ours.
+    import numpy as np
+    import oracle
+    man["divergences"] = []
+    hraw = bytes(corpus.generate("json", 11, 20000))
+    rng = np.random.default_rng(2026)
+    want = {"huf_leftover_bits": None, "err_huf_ran_out_checksum": None, "div_huf_ran_out_no_checksum": None}
+    for checksum in (False, True):
+        hfr = z.compress(hraw, 3, checksum=checksum)
+        for _ in range(4000):
+            bb = bytearray(hfr)
+            pos = int(rng.integers(40, len(bb) // 3))          # the literals section comes first in the block
+            bb[pos] ^= 1 << int(rng.integers(0, 8))
+            ref, rerr = z.decompress_oneshot(bytes(bb), 65536)
+            out, err = oracle.decompress(bytes(bb), 65536)
+            if not checksum and rerr == 0 and err == 0 and ref != hraw and want["huf_leftover_bits"] is None:
+                want["huf_leftover_bits"] = (bytes(bb), ref)
+            if not checksum and rerr == 0 and err == 20 and want["div_huf_ran_out_no_checksum"] is None:
+                want["div_huf_ran_out_no_checksum"] = (bytes(bb), ref)
+            if checksum and rerr == 22 and err == 22 and want["err_huf_ran_out_checksum"] is None:
+                # make sure it is the literals that differ, not the trailer: the same flip without the verdict rule is -20
+                want["err_huf_ran_out_checksum"] = (bytes(bb), None)
+            if all(v is not None for v in want.values()):
+                break
+    assert all(v is not None for v in want.values()), want
+    fr_l, ref_l = want["huf_leftover_bits"]
+    assert oracle.decompress(fr_l, 65536) == (ref_l, 0)
+    add("huf_leftover_bits", fr_l, ref_l, "a flipped bit leaves bits over in a Huffman stream: libzstd's fast loops accept, same bytes", keep_raw=False)
+    add_err("err_huf_ran_out_checksum", want["err_huf_ran_out_checksum"][0],
+            "a Huffman stream runs out of bits, frame with checksum: libzstd makes up literals and reports -22")
+    fr_d, ref_d = want["div_huf_ran_out_no_checksum"]
+    with open(os.path.join(OUT, "div_huf_ran_out_no_checksum.zst"), "wb") as f:
+        f.write(fr_d)
+    man["divergences"].append({"name": "div_huf_ran_out_no_checksum", "libzstd_error": 0, "libzstd_out_sha256": hashlib.sha256(ref_d).hexdigest(),
+                               "ours": 20, "note": "a Huffman stream runs out of bits, no checksum: libzstd accepts made-up literals, "
+                                                   "the oracle and the GPU path report corruption_detected (documented)"})
+
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(man, f, indent=1)
     tot = sum(os.path.getsize(os.path.join(OUT, x)) for x in os.listdir(OUT))

@@ -232,6 +232,7 @@ extern "C" int kzs_decompress_batch(const u8* src_in, u64 src_len, const u64* sr
                 if (!st && op != blk.regen) st = KZG_E_GENERIC;
             }
         }
+        if (!st && fr.lit_garbage) st = fr.checksum_off != KZG_NONE ? KZG_E_CHECKSUM_WRONG : KZG_E_CORRUPTION;
         if (!st && fr.checksum_off != KZG_NONE) {
             if ((u32)xxh64(fdst, fr.out_size) != kzg_rd32(src + src_off[f] + fr.checksum_off)) st = KZG_E_CHECKSUM_WRONG;
         }

@@ -46,6 +46,15 @@ def test_golden_error_vectors(dec, manifest):
         assert s == expect[n], (n, s)
 
 
+def test_documented_divergences(dec, manifest):
+    """Where this decoder deliberately differs from libzstd: a Huffman stream that runs out of bits in
+    a frame without checksum -- libzstd makes up literals and accepts, the GPU path reports corruption_detected."""
+    ds = manifest["divergences"]
+    _, status, _ = run(dec, [gbytes(d["name"] + ".zst") for d in ds], [1 << 16] * len(ds))
+    for d, s in zip(ds, status):
+        assert s == d["ours"], (d["name"], s)
+
+
 @pytest.mark.parametrize("kind,level,checksum", [("logs", 3, False), ("json", 3, True), ("literal", 1, False), ("random", 3, False)])
 def test_corpora_against_oracle_and_libzstd(dec, oracle_mod, libzstd, kind, level, checksum):
     import corpus

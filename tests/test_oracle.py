@@ -46,6 +46,16 @@ def test_golden_error_vectors(oracle_mod, manifest):
             assert err == 72, e["name"]
 
 
+def test_documented_divergences(oracle_mod, libzstd, manifest):
+    """Frames on which the oracle (and the GPU path held to it) deliberately differ from libzstd: see DESIGN.md section 7."""
+    for d in manifest["divergences"]:
+        data = gbytes(d["name"] + ".zst")
+        ref, rerr = libzstd.decompress_oneshot(data, 1 << 20)
+        assert rerr == d["libzstd_error"] and hashlib.sha256(ref).hexdigest() == d["libzstd_out_sha256"]
+        _, err = oracle_mod.decompress(data, 1 << 20)
+        assert err == d["ours"], d["name"]
+
+
 def test_xxh64_against_xxhash(oracle_mod):
     import xxhash
     rng = np.random.default_rng(1)
@@ -106,26 +116,31 @@ def _literal_section(fr, oracle_mod):
 
 
 def test_random_bitflips_agree_with_libzstd(oracle_mod, libzstd):
-    """Corrupt frames: outside Huffman-coded literals the oracle and libzstd must agree exactly
-    (accept with identical bytes, or both reject).  Inside the literals section the oracle is
-    deliberately spec-strict: RFC 8878 4.2.2 requires every Huffman stream to be consumed exactly,
-    libzstd 1.5.7's fast Huffman loop does not verify that and may accept garbage."""
+    """Corrupt frames: the oracle and libzstd 1.5.7 agree on the verdict and, when both accept, on every byte -- with one
+    documented exception: a Huffman stream that RUNS OUT of bits in a block libzstd
+    decodes with its fast four-stream loops.  libzstd makes up literals from a stale bit container there; the oracle (and
+    the GPU path) reject such a frame when it has no checksum (corruption_detected) and report checksum_wrong, as libzstd
+    does, when it has one.  Left-over bits in those loops are accepted like libzstd, with identical bytes."""
     import corpus
     rng = np.random.default_rng(7)
     raw = bytes(corpus.generate("json", 11, 20000))
-    fr = libzstd.compress(raw, 3)
-    lit_lo, lit_hi = _literal_section(fr, oracle_mod)
-    n_strict = 0
-    for _ in range(600):
-        b = bytearray(fr)
-        p = int(rng.integers(4, len(b)))
-        b[p] ^= 1 << int(rng.integers(0, 8))
-        ref, rerr = libzstd.decompress_oneshot(bytes(b), 65536)
-        out, err = oracle_mod.decompress(bytes(b), 65536)
-        if lit_lo <= p < lit_hi and rerr == 0 and err == 20:
-            n_strict += 1
-            continue
-        assert (rerr == 0) == (err == 0), (p, rerr, err)
-        if rerr == 0:
-            assert out == ref, p
-    assert n_strict < 600
+    for checksum in (False, True):
+        fr = libzstd.compress(raw, 3, checksum=checksum)
+        lit_lo, lit_hi = _literal_section(fr, oracle_mod)
+        n_made_up = n_accept = 0
+        for _ in range(600):
+            b = bytearray(fr)
+            p = int(rng.integers(4, len(b)))
+            b[p] ^= 1 << int(rng.integers(0, 8))
+            ref, rerr = libzstd.decompress_oneshot(bytes(b), 65536)
+            out, err = oracle_mod.decompress(bytes(b), 65536)
+            if not checksum and lit_lo <= p < lit_hi and rerr == 0 and err == 20:
+                n_made_up += 1          # the documented exception
+                continue
+            if rerr == 70 and err == 20:
+                continue                # libzstd notices the missing room first (dstSize_tooSmall); both reject
+            assert rerr == err, (checksum, p, rerr, err)
+            if rerr == 0:
+                n_accept += 1
+                assert out == ref, p
+        assert n_made_up < 60 and (checksum or n_accept > 100), (n_made_up, n_accept)
