@@ -70,7 +70,11 @@ size_t kzg_write_seek_table(void* dst, size_t cap, const uint64_t* comp_size, co
  *   d_src + d_src_off[i], d_src_size[i]   exactly one zstd (or skippable) frame each
  *   d_dst + d_dst_off[i], d_dst_cap[i]    where its output goes and how much room there is
  *   d_status[i]                           out: 0 or ZSTD_ErrorCode (20 corruption, 22 checksum, 70 dst too small...)
- *   d_out_size[i]                         out: decoded bytes
+ *   d_out_size[i]                         out: decoded bytes.  For a frame that failed: the index of the block the error
+ *                                         belongs to (the blocks before it are good: the streaming layer hands them over
+ *                                         first, as libzstd does); for status 22 the decoded size -- the content is in place,
+ *                                         its checksum does not match -- unless bit 63 is set (then: block index, see
+ *                                         DESIGN.md "Error behaviour")
  * All pointers are device pointers; the 16-byte aligned chunks around every byte of d_src must be
  * readable (true for any cudaMalloc allocation).  total_src_bytes / total_dst_cap / max_frame_dst_cap
  * are host-side sums / max of the table, used to size the workspace.  Work is enqueued on
@@ -111,6 +115,33 @@ int kzg_last_batch_stats(kzg_ctx* ctx, kzg_batch_stats* out);
  * carries a dictionary ID that frames naming another ID are rejected against (dictionary_wrong, 32).
  * Replaces ZSTD_DCtx_loadDictionary (Wrapper.cpp:58-73) on the batch layer. */
 int kzg_ctx_set_dictionary(kzg_ctx* ctx, const void* dict, size_t size);
+
+/* ---- A frame decoded in SEGMENTS (what lets the streaming shim below hand over output block by block, as
+ * ZSTD_decompressStream does, with memory bounded by the window): a segment is a run of whole blocks of one frame, in
+ * order.  The state carries what the next segment needs from the previous ones -- the entropy tables that "repeat" and
+ * "treeless" modes refer to, the three repeat offsets, and the running XXH64 of the content.  The caller keeps the last
+ * `window` bytes of output and passes them as `history`.
+ *   kzg_segment_begin   state at the start of a frame (tables / offsets / history prefix come from `dict`, if any);
+ *                       returns the number of dictionary content bytes (the initial history is the end of `dict`)
+ *   kzg_decompress_segment_host   blocks: the segment's blocks with their 3-byte headers; last_hdr_off: offset of the
+ *                       last block's header in it (its Last_Block bit is forced on in a private copy);
+ *                       *status / *out_size as in the batch calls; the state is advanced only when *status == 0
+ *   kzg_segment_checksum          low 32 bits of the XXH64 of everything decoded since kzg_segment_begin */
+typedef struct kzg_seg_state {
+    uint32_t owner_kind[4];       /* Huffman, LL, OF, ML tables: 0 none yet, 1 predefined, 2 the description below */
+    uint32_t rep[3];
+    uint32_t block_max;           /* Block_Maximum_Size of the frame */
+    uint64_t xxh_acc[4], xxh_total;
+    uint8_t xxh_tail[32];         /* content bytes not yet folded into the accumulators (xxh_total % 32 of them) */
+    uint32_t want_checksum, digest;   /* digest: low 32 bits of the XXH64 of the content so far (kept current by every segment) */
+    uint64_t fse_desc[50];        /* KzgFseDesc */
+    uint64_t huf_desc[34];        /* KzgHufDesc */
+} kzg_seg_state;
+long long kzg_segment_begin(kzg_seg_state* st, uint32_t block_max, int want_checksum, const void* dict, size_t dict_size);
+int kzg_decompress_segment_host(kzg_ctx* ctx, kzg_seg_state* st, const void* blocks, size_t blocks_size, size_t last_hdr_off,
+                                const void* history, size_t history_size, void* dst, size_t dst_cap,
+                                uint32_t* status, uint64_t* out_size);
+uint32_t kzg_segment_checksum(const kzg_seg_state* st);
 
 /* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline).
  * kzg_last_stage_ms fills ms[i] / names[i] for the stages of the last finished batch and returns

@@ -40,6 +40,7 @@ EXPORTS = [
     "kzg_compress_batch_host", "kzg_enc_set_profiling", "kzg_enc_last_stage_ms",
     "kzg_createCCtx", "kzg_freeCCtx", "kzg_CCtx_setParameter", "kzg_CCtx_loadDictionary", "kzg_compressStream2",
     "kzg_seek_table_bound", "kzg_write_seek_table",
+    "kzg_segment_begin", "kzg_decompress_segment_host", "kzg_segment_checksum",
 ]
 
 _lib = None

@@ -62,6 +62,11 @@ struct kzg_ctx {
     u64 last_n_frames = 0;
     // staging for the host-pointer form
     DevBuf st_src, st_dst, st_tab;
+    // segment mode (kzg_decompress_segment_host): how the next batch's only frame starts
+    bool seg_on = false;
+    u32 seg_init_owner[4] = { 0, 0, 0, 0 }, seg_block_max = 0;
+    DevBuf seg_xxh;
+    std::vector<u8> seg_frame;
     // raw-content dictionary applied to every frame of subsequent batches
     DevBuf dict;                   // dictionary content (history prefix)
     u32 dict_size = 0;
@@ -182,6 +187,41 @@ extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
 // ZSTD_DCtx_loadDictionary at Wrapper.cpp:58-73).  A raw-content dictionary is a history prefix.  A formatted
 // dictionary (magic 0xEC30A437: dictID, Huffman table, OF / ML / LL FSE tables, three repeat offsets, content;
 // libzstd ZSTD_loadDEntropy order) also preloads every frame's entropy tables and repeat offsets.
+// Parses a dictionary: a formatted one (magic 0xEC30A437: dictID, Huffman table, OF / ML / LL FSE tables, three repeat
+// offsets, content; libzstd ZSTD_loadDEntropy order) fills fd / hd / rep / id and sets *entropy; any other buffer is
+// raw content.  Returns the offset of the content inside `dict`, or a negative code.
+static long long parse_dictionary(const void* dict, size_t size, KzgFseDesc& fd, KzgHufDesc& hd, u32 rep[3], u32& id, u32& entropy) {
+    const u8* p = (const u8*)dict;
+    const u8* const end = p + size;
+    id = 0; entropy = 0; rep[0] = 1; rep[1] = 4; rep[2] = 8;
+    memset(&fd, 0, sizeof fd);
+    memset(&hd, 0, sizeof hd);
+    if (size >= 8 && kzg_rd32(p) == KZG_DICT_MAGIC) {
+        id = kzg_rd32(p + 4);
+        p += 8;
+        const u32 hsz = kzg_read_huf_weights(p, (u32)(end - p), hd.weight, hd.nsym, hd.maxbits);
+        if (hsz == 0) return -(long long)KZG_E_DICT_CORRUPTED;
+        p += hsz;
+        const u32 order[3] = { 1, 2, 0 }, max_sym[3] = { 35, 31, 52 }, max_log[3] = { 9, 8, 9 };   // stored as OF, ML, LL
+        for (u32 k = 0; k < 3; k++) {
+            const u32 t = order[k];
+            u32 nsym = 0, log = 0;
+            const u32 h = kzg_read_ncount(p, (u32)(end - p), max_sym[t], max_log[t], fd.norm[t], nsym, log);
+            if (h == 0) return -(long long)KZG_E_DICT_CORRUPTED;
+            fd.kind[t] = 2; fd.log[t] = (u8)log; fd.nsym[t] = (u8)nsym;
+            p += h;
+        }
+        if (p + 12 > end) return -(long long)KZG_E_DICT_CORRUPTED;
+        for (u32 k = 0; k < 3; k++) {
+            rep[k] = kzg_rd32(p + 4 * k);
+            if (rep[k] == 0 || rep[k] > (u64)(end - (p + 12))) return -(long long)KZG_E_DICT_CORRUPTED;
+        }
+        p += 12;
+        entropy = 1;
+    }
+    return (long long)(p - (const u8*)dict);
+}
+
 extern "C" int kzg_ctx_set_dictionary(kzg_ctx* c, const void* dict, size_t size) {
     if (!c) return -(int)KZG_E_GENERIC;
     std::lock_guard<std::mutex> lock(c->mu);
@@ -189,39 +229,17 @@ extern "C" int kzg_ctx_set_dictionary(kzg_ctx* c, const void* dict, size_t size)
     if (size > 0x7FFFFFFFu) return -(int)KZG_E_MEMORY;
     if (c->dict_host.size() == size && memcmp(c->dict_host.data(), dict, size) == 0) return 0;
     CK(cudaSetDevice(c->device));
-    const u8* p = (const u8*)dict;
-    const u8* const end = p + size;
-    u32 id = 0, entropy = 0, rep[3] = { 1, 4, 8 };
-    if (size >= 8 && kzg_rd32(p) == KZG_DICT_MAGIC) {
-        KzgFseDesc fd;                       // (on the stack: contexts load dictionaries concurrently)
-        KzgHufDesc hd;
-        memset(&fd, 0, sizeof fd);
-        memset(&hd, 0, sizeof hd);
-        id = kzg_rd32(p + 4);
-        p += 8;
-        const u32 hsz = kzg_read_huf_weights(p, (u32)(end - p), hd.weight, hd.nsym, hd.maxbits);
-        if (hsz == 0) return -(int)KZG_E_DICT_CORRUPTED;
-        p += hsz;
-        const u32 order[3] = { 1, 2, 0 }, max_sym[3] = { 35, 31, 52 }, max_log[3] = { 9, 8, 9 };   // stored as OF, ML, LL
-        for (u32 k = 0; k < 3; k++) {
-            const u32 t = order[k];
-            u32 nsym = 0, log = 0;
-            const u32 h = kzg_read_ncount(p, (u32)(end - p), max_sym[t], max_log[t], fd.norm[t], nsym, log);
-            if (h == 0) return -(int)KZG_E_DICT_CORRUPTED;
-            fd.kind[t] = 2; fd.log[t] = (u8)log; fd.nsym[t] = (u8)nsym;
-            p += h;
-        }
-        if (p + 12 > end) return -(int)KZG_E_DICT_CORRUPTED;
-        for (u32 k = 0; k < 3; k++) {
-            rep[k] = kzg_rd32(p + 4 * k);
-            if (rep[k] == 0 || rep[k] > (u64)(end - (p + 12))) return -(int)KZG_E_DICT_CORRUPTED;
-        }
-        p += 12;
-        entropy = 1;
+    KzgFseDesc fd;                           // (on the stack: contexts load dictionaries concurrently)
+    KzgHufDesc hd;
+    u32 id = 0, entropy = 0, rep[3];
+    const long long coff = parse_dictionary(dict, size, fd, hd, rep, id, entropy);
+    if (coff < 0) return (int)coff;
+    if (entropy) {
         CK(cudaMemcpy((u8*)c->consts.p + offsetof(KzgConsts, dict_fse), &fd, sizeof fd, cudaMemcpyHostToDevice));
         CK(cudaMemcpy((u8*)c->consts.p + offsetof(KzgConsts, dict_huf), &hd, sizeof hd, cudaMemcpyHostToDevice));
     }
-    const size_t content = (size_t)(end - p);
+    const u8* p = (const u8*)dict + coff;
+    const size_t content = size - (size_t)coff;
     if (c->dict.ensure(content + 16)) return -(int)KZG_E_MEMORY;
     if (content) CK(cudaMemcpy(c->dict.p, p, content, cudaMemcpyHostToDevice));
     c->dict_host.assign((const u8*)dict, (const u8*)dict + size);
@@ -420,6 +438,10 @@ static int enqueue_batch(kzg_ctx* c, const void* d_src, const uint64_t* d_src_of
     b.dict = (const u8*)c->dict.p; b.dict_size = c->dict_size; b.dict_id = c->dict_id;
     b.dict_entropy = c->dict_entropy;
     b.dict_rep[0] = c->dict_rep[0]; b.dict_rep[1] = c->dict_rep[1]; b.dict_rep[2] = c->dict_rep[2];
+    if (c->seg_on) {
+        b.seg_mode = 1; b.seg_block_max = c->seg_block_max;
+        for (int t = 0; t < 4; t++) b.init_owner[t] = c->seg_init_owner[t];
+    }
     CK(cudaMemsetAsync(c->ctr.p, 0, sizeof(KzgCounters), stream));
     const int launches = kzg_launch_batch(b, c->sm_count, stream, c->profiling ? c->ev : nullptr);
     c->ev_valid = c->profiling;
@@ -507,6 +529,10 @@ extern "C" int kzg_last_batch_stats(kzg_ctx* c, kzg_batch_stats* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+static int batch_host_locked(kzg_ctx* c, const void* src, const uint64_t* src_off, const uint64_t* src_size,
+                             void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n,
+                             uint32_t* status, uint64_t* out_size);
+
 extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint64_t* src_off, const uint64_t* src_size,
                                          void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n,
                                          uint32_t* status, uint64_t* out_size) {
@@ -514,6 +540,12 @@ extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint
     if (n == 0) return 0;
     if (n > 0xFFFFFFF0ull) return -(int)KZG_E_GENERIC;
     std::lock_guard<std::mutex> lock(c->mu);
+    return batch_host_locked(c, src, src_off, src_size, dst, dst_off, dst_cap, n, status, out_size);
+}
+
+static int batch_host_locked(kzg_ctx* c, const void* src, const uint64_t* src_off, const uint64_t* src_size,
+                             void* dst, const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t n,
+                             uint32_t* status, uint64_t* out_size) {
     CK(cudaSetDevice(c->device));
     // extent of the source / destination spans
     u64 src_lo = ~0ull, src_hi = 0, dst_lo = ~0ull, dst_hi = 0, tot_dst = 0;
@@ -628,4 +660,112 @@ extern "C" int kzg_decompress_batch_host(kzg_ctx* c, const void* src, const uint
     c->last_launches = launches_total;
     free(h_tab);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A frame decoded in segments (include/kzg.h).  A segment runs through the very same batch pipeline as a synthetic
+// frame -- magic, a header without content size / checksum / dictionary ID, the blocks -- in "segment mode": the tables
+// that repeat / treeless modes refer to, the repeat offsets and the history come from the state instead of a frame
+// start.  Afterwards the state is advanced from what the link and offsets stages left in the frame descriptor.
+static_assert(sizeof(((kzg_seg_state*)0)->fse_desc) == sizeof(KzgFseDesc), "kzg_seg_state.fse_desc holds a KzgFseDesc");
+static_assert(sizeof(((kzg_seg_state*)0)->huf_desc) == sizeof(KzgHufDesc), "kzg_seg_state.huf_desc holds a KzgHufDesc");
+
+extern "C" long long kzg_segment_begin(kzg_seg_state* st, uint32_t block_max, int want_checksum, const void* dict, size_t dict_size) {
+    if (!st) return -(long long)KZG_E_GENERIC;
+    memset(st, 0, sizeof *st);
+    st->rep[0] = 1; st->rep[1] = 4; st->rep[2] = 8;
+    st->block_max = block_max;
+    st->want_checksum = want_checksum ? 1u : 0u;
+    st->xxh_acc[0] = 0x9E3779B185EBCA87ull + 0xC2B2AE3D27D4EB4Full; st->xxh_acc[1] = 0xC2B2AE3D27D4EB4Full;
+    st->xxh_acc[2] = 0; st->xxh_acc[3] = 0ull - 0x9E3779B185EBCA87ull;
+    st->digest = 0x51D8E999u;                 // low half of XXH64 of the empty input
+    if (!dict || dict_size == 0) return 0;
+    KzgFseDesc fd;
+    KzgHufDesc hd;
+    u32 id = 0, entropy = 0, rep[3];
+    const long long coff = parse_dictionary(dict, dict_size, fd, hd, rep, id, entropy);
+    if (coff < 0) return coff;
+    if (entropy) {
+        memcpy(st->fse_desc, &fd, sizeof fd);
+        memcpy(st->huf_desc, &hd, sizeof hd);
+        st->owner_kind[0] = st->owner_kind[1] = st->owner_kind[2] = st->owner_kind[3] = 2;
+        st->rep[0] = rep[0]; st->rep[1] = rep[1]; st->rep[2] = rep[2];
+    }
+    return (long long)dict_size - coff;
+}
+
+extern "C" uint32_t kzg_segment_checksum(const kzg_seg_state* st) { return st ? st->digest : 0u; }
+
+extern "C" int kzg_decompress_segment_host(kzg_ctx* c, kzg_seg_state* st, const void* blocks, size_t blocks_size, size_t last_hdr_off,
+                                           const void* history, size_t history_size, void* dst, size_t dst_cap,
+                                           uint32_t* status, uint64_t* out_size) {
+    if (!c || !st || !blocks || !status || !out_size || blocks_size < 3 || last_hdr_off + 3 > blocks_size) return -(int)KZG_E_GENERIC;
+    if (history_size > 0x7FFFFFFFu || blocks_size > 0x7FFFFFF0u) return -(int)KZG_E_MEMORY;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CK(cudaSetDevice(c->device));
+    // the synthetic frame: magic | descriptor 0 (window descriptor follows; no content size, checksum, dictionary ID) |
+    // window descriptor (the block size limit comes from the state) | blocks, the last one marked last
+    try { c->seg_frame.resize(6 + blocks_size); } catch (const std::bad_alloc&) { return -(int)KZG_E_MEMORY; }
+    u8* f = c->seg_frame.data();
+    f[0] = 0x28; f[1] = 0xB5; f[2] = 0x2F; f[3] = 0xFD; f[4] = 0x00; f[5] = 0x00;
+    memcpy(f + 6, blocks, blocks_size);
+    f[6 + last_hdr_off] |= 1u;
+    // history and tables
+    if (c->dict.ensure(history_size + 16)) return -(int)KZG_E_MEMORY;
+    if (history_size) CK(cudaMemcpy(c->dict.p, history, history_size, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((u8*)c->consts.p + offsetof(KzgConsts, dict_fse), st->fse_desc, sizeof(KzgFseDesc), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((u8*)c->consts.p + offsetof(KzgConsts, dict_huf), st->huf_desc, sizeof(KzgHufDesc), cudaMemcpyHostToDevice));
+    c->dict_host.clear();                     // (whatever dictionary was loaded is gone: the next kzg_ctx_set_dictionary reloads)
+    c->dict_size = (u32)history_size; c->dict_id = 0; c->dict_entropy = 1;
+    c->dict_rep[0] = st->rep[0]; c->dict_rep[1] = st->rep[1]; c->dict_rep[2] = st->rep[2];
+    c->seg_on = true; c->seg_block_max = st->block_max;
+    for (int t = 0; t < 4; t++)
+        c->seg_init_owner[t] = st->owner_kind[t] == 2 ? KZG_DICT_OWNER : (st->owner_kind[t] == 1 && t ? KZG_NONE : KZG_INVALID_OWNER);
+    const uint64_t off0 = 0, size0 = 6 + blocks_size, cap0 = dst_cap;
+    int rc = batch_host_locked(c, f, &off0, &size0, dst, &off0, &cap0, 1, status, out_size);
+    c->seg_on = false;
+    c->dict_size = 0; c->dict_entropy = 0; c->dict_rep[0] = 1; c->dict_rep[1] = 4; c->dict_rep[2] = 8;
+    if (rc < 0) return rc;
+    if (*status != 0) return 0;
+    // ---- advance the state: table owners and repeat offsets the link / offsets stages left in the frame descriptor
+    KzgFrame fr;
+    CK(cudaMemcpy(&fr, c->frames.p, sizeof fr, cudaMemcpyDeviceToHost));
+    KzgFseDesc fd;
+    memcpy(&fd, st->fse_desc, sizeof fd);
+    for (int t = 0; t < 4; t++) {
+        const u32 o = fr.end_owner[t];
+        if (o == KZG_DICT_OWNER) continue;                       // unchanged by this segment
+        if (o == KZG_INVALID_OWNER) { st->owner_kind[t] = 0; continue; }
+        if (o == KZG_NONE) { st->owner_kind[t] = 1; continue; }
+        if (t == 0) CK(cudaMemcpy(st->huf_desc, (const u8*)c->huf.p + (size_t)o * sizeof(KzgHufDesc), sizeof(KzgHufDesc), cudaMemcpyDeviceToHost));
+        else {
+            KzgFseDesc src;
+            CK(cudaMemcpy(&src, (const u8*)c->fse.p + (size_t)o * sizeof(KzgFseDesc), sizeof src, cudaMemcpyDeviceToHost));
+            const int k = t - 1;
+            memcpy(fd.norm[k], src.norm[k], sizeof fd.norm[k]);
+            fd.log[k] = src.log[k]; fd.nsym[k] = src.nsym[k]; fd.kind[k] = src.kind[k];
+        }
+        st->owner_kind[t] = 2;
+    }
+    memcpy(st->fse_desc, &fd, sizeof fd);
+    st->rep[0] = fr.end_rep[0]; st->rep[1] = fr.end_rep[1]; st->rep[2] = fr.end_rep[2];
+    // ---- the running checksum: the segment's output is still in the device staging buffer
+    if (st->want_checksum) {
+        if (c->seg_xxh.ensure(sizeof(KzgXxhState))) return -(int)KZG_E_MEMORY;
+        KzgXxhState xs;
+        memcpy(xs.acc, st->xxh_acc, sizeof xs.acc);
+        xs.total = st->xxh_total;
+        memcpy(xs.tail, st->xxh_tail, 32);
+        xs.want = 1; xs.digest = st->digest;
+        CK(cudaMemcpyAsync(c->seg_xxh.p, &xs, sizeof xs, cudaMemcpyHostToDevice, c->own_stream));
+        kzg_launch_xxh_segment((KzgXxhState*)c->seg_xxh.p, (const u8*)c->st_dst.p, *out_size, c->own_stream);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&xs, c->seg_xxh.p, sizeof xs, cudaMemcpyDeviceToHost, c->own_stream));
+        CK(cudaStreamSynchronize(c->own_stream));
+        memcpy(st->xxh_acc, xs.acc, sizeof xs.acc);
+        st->xxh_total = xs.total;
+        memcpy(st->xxh_tail, xs.tail, 32);
+        st->digest = xs.digest;
+    }
+    return 0;
 }

@@ -77,6 +77,11 @@ struct KzgFrame {           // one per input frame
     u32 block_max;
     u32 xxh_lo;             // low 32 bits of XXH64 computed by the checksum kernel
     u32 lit_garbage;        // a block's Huffman stream ran out of bits where libzstd's fast loops make up literals (see kzg_huf_verdict)
+    u32 fail_block;         // status != 0: index (in the frame) of the block the error belongs to; the blocks before it are good
+    // entropy state after the last block, for a frame that is decoded in segments (kzg_decompress_segment_host):
+    u32 end_owner[4];       // table owners: Huffman, LL, OF, ML (a compressed block, KZG_NONE, KZG_DICT_OWNER or KZG_INVALID_OWNER)
+    u32 end_rep[3];         // repeat offsets
+    u32 pad_;
 };
 
 struct KzgBlock {           // one per block of every frame
@@ -166,6 +171,12 @@ struct KzgBatch {
     u32 n_frames;
     u32 tile_bytes;     // shared-memory output tile of the execute kernel (>= largest block)
     u32 big_by_cta;     // frames of many blocks are left to the CTA-per-frame execute kernel (set at launch)
+    // segment mode (a frame decoded piece by piece behind the streaming shim): the batch is one synthetic frame that
+    // continues a real one -- its tables start from init_owner[] (Huffman, LL, OF, ML), its repeat offsets from dict_rep[],
+    // its history is `dict`, and the block size limit is the real frame's
+    u32 seg_mode;
+    u32 init_owner[4];
+    u32 seg_block_max;
     // workspace
     KzgFrame* frames;
     KzgBlock* blocks;

@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch
         // frames of many blocks (large windows, long matches) go straight to the full variant, which keeps medium-long
         // matches inside the window
         bool deferred = !FULL && nblk > KZG_EX_BIG_FRAME_BLOCKS;
+        u32 kfail = 0;
         for (u32 k = 0; k < nblk && !failed && !deferred; k++) {
             const KzgBlock blk = B.blocks[first + k];
             u8* out = fdst + blk.out_off;
@@ -563,12 +564,13 @@ __global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch
                     const u32 r = kzg_exec_sequences<FULL>(B, blk, cb, out, smem, lane);
                     failed = r == 1;
                     deferred = r == 2;
+                    kfail = k;
                 }
             }
             __threadfence_block();
             __syncwarp();
         }
-        if (failed && lane == 0) B.frames[f].status = KZG_E_CORRUPTION;
+        if (failed && lane == 0) { B.frames[f].status = KZG_E_CORRUPTION; B.frames[f].fail_block = kfail; }
         // the full variant redoes a frame with long runs; a frame of many blocks goes to the CTA-per-frame kernel
         if (deferred && lane == 0) B.dlist[atomicAdd(&B.ctr->n_defer, 1u)] = f | ((B.big_by_cta && nblk > KZG_EX_BIG_FRAME_BLOCKS) ? KZG_DEFER_BIG : 0u);
     }

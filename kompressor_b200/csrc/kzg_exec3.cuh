@@ -193,6 +193,7 @@ KZG_SIMT_D void kzg_exec3_warp(const KzgBatch& B, u32 sb, u32 lane) {
                 // (the sequence kernel guarantees non-decreasing lit_end / out_end within the block limits)
                 if (off - 1u >= KZG_OFF_INVALID - 1u || off > cc + rl - cph) {      // no dictionary here: nothing before the frame
                     B.frames[cf].status = KZG_E_CORRUPTION;
+                    B.frames[cf].fail_block = bk;
                     emit((K_END << 30), 0u, 0u, 0u);
                     st = ST_FRAME;
                     return true;

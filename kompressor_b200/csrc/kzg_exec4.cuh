@@ -307,14 +307,15 @@ __global__ void __launch_bounds__(KZG_X4_THREADS, 1) kzg_exec4_kernel(KzgBatch B
         u8* const fdst = B.dst + B.dst_off[f];
         const u32 nblk = fr->n_blocks, first = fr->first_block;
         bool failed = false;
+        u32 kfail = 0;
         for (u32 k = 0; k < nblk && !failed; k++) {
             const KzgBlock blk = B.blocks[first + k];
             // raw / RLE blocks and literal-only blocks were written by kzg_bulk_kernel
             if (blk.type == 2) {
                 const KzgCBlock* cb = &B.cblocks[blk.cidx];
-                if (cb->n_seq) failed = kzg_exec4_block(B, blk, cb, fdst + blk.out_off, smem) == 1u;
+                if (cb->n_seq) { failed = kzg_exec4_block(B, blk, cb, fdst + blk.out_off, smem) == 1u; kfail = k; }
             }
         }
-        if (failed && threadIdx.x == 0) B.frames[f].status = KZG_E_CORRUPTION;
+        if (failed && threadIdx.x == 0) { B.frames[f].status = KZG_E_CORRUPTION; B.frames[f].fail_block = kfail; }
     }
 }

@@ -148,7 +148,77 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
         B.frames[f].xxh_lo = (u32)h;
     }
     B.status[f] = status;
-    B.out_size[f] = status == KZG_OK ? len : 0;
+    // on an error: the index of the block it belongs to (the blocks before it are good; the streaming shim hands them over
+    // first, as libzstd does) -- except for a checksum that does not match: the whole content is there
+    // (bit 63 marks the one checksum verdict that comes without the content: literals libzstd would have made up)
+    B.out_size[f] = status == KZG_OK || (status == KZG_E_CHECKSUM_WRONG && !fr->lit_garbage) ? len
+                    : ((u64)fr->fail_block | (status == KZG_E_CHECKSUM_WRONG ? 1ull << 63 : 0ull));
+}
+
+// ------------------------------------------------------------------------------------------------
+// XXH64 over a stream that arrives in segments: the four accumulators on four lanes as above; up to 31 bytes that do
+// not fill a 32-byte stripe wait in the state.  The digest (as if the stream ended here) is recomputed every time.
+__global__ void __launch_bounds__(32) kzg_xxh_segment_kernel(KzgXxhState* S, const u8* data, u64 len) {
+    const u32 q = threadIdx.x & 31;
+    const u32 t = (u32)(S->total & 31ull);                 // bytes waiting in the state
+    const u64 all = (u64)t + len, stripes = all >> 5;
+    u64 acc = q < 4 ? S->acc[q] : 0ull;
+    auto logical = [&](u64 p) -> u32 { return p < t ? (u32)S->tail[p] : (u32)data[p - t]; };
+    if (q < 4 && stripes) {
+        u64 k = 0;
+        if (t) {                                           // the first stripe starts in the waiting bytes
+            u64 x = 0;
+            for (int b = 0; b < 8; b++) x |= (u64)logical(8 * q + b) << (8 * b);
+            acc = kzg_xxround(acc, x);
+            k = 1;
+        }
+        const u8* s = data + (t ? 32 - t : 0) + 8 * q;      // stripe k (k >= 1 if t) starts at data offset 32 * k - t
+        const u64 rest = stripes - k;
+        u64 j = 0;
+        for (; j + 16 <= rest; j += 16) {
+            u64 x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = kzg_ld64_any(s + 32 * (j + i));
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc = kzg_xxround(acc, x[i]);
+        }
+        for (; j < rest; j++) acc = kzg_xxround(acc, kzg_ld64_any(s + 32 * j));
+    }
+    __syncwarp();
+    // the bytes that wait now: logical positions [32 * stripes, all)
+    const u32 nt = (u32)(all & 31ull);
+    u32 tb = 0;
+    if (q < nt) tb = logical((stripes << 5) + q);
+    __syncwarp();
+    if (q < nt) S->tail[q] = (u8)tb;
+    if (q < 4) S->acc[q] = acc;
+    const u64 total = S->total + len;
+    const u64 v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2),
+              v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+    __syncwarp();
+    if (q == 0) {
+        S->total = total;
+        u64 h;
+        if (total >= 32) {
+            h = kzg_rotl64(v1, 1) + kzg_rotl64(v2, 7) + kzg_rotl64(v3, 12) + kzg_rotl64(v4, 18);
+            h = (h ^ kzg_xxround(0, v1)) * XP1 + XP4;
+            h = (h ^ kzg_xxround(0, v2)) * XP1 + XP4;
+            h = (h ^ kzg_xxround(0, v3)) * XP1 + XP4;
+            h = (h ^ kzg_xxround(0, v4)) * XP1 + XP4;
+        } else h = XP5;
+        h += total;
+        const u8* c = S->tail;
+        const u8* e = c + nt;
+        while (e - c >= 8) { h = kzg_rotl64(h ^ kzg_xxround(0, kzg_rd64(c)), 27) * XP1 + XP4; c += 8; }
+        if (e - c >= 4) { h = kzg_rotl64(h ^ ((u64)kzg_rd32(c) * XP1), 23) * XP2 + XP3; c += 4; }
+        while (c < e) { h = kzg_rotl64(h ^ ((u64)(*c) * XP5), 11) * XP1; c++; }
+        h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+        S->digest = (u32)h;
+    }
+}
+
+void kzg_launch_xxh_segment(KzgXxhState* d_state, const u8* d_data, u64 len, cudaStream_t stream) {
+    kzg_xxh_segment_kernel<<<1, 32, 0, stream>>>(d_state, d_data, len);
 }
 
 // ------------------------------------------------------------------------------------------------

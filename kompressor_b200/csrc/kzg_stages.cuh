@@ -34,6 +34,9 @@ KZG_HD void kzg_stage_scan(const KzgBatch& B, u32 i) {
     KzgFrame fr;
     fr.window_size = 0; fr.fcs = ~0ull; fr.out_size = 0; fr.first_block = 0; fr.n_blocks = 0;
     fr.hdr_size = 0; fr.dict_id = 0; fr.checksum_off = KZG_NONE; fr.status = KZG_OK; fr.block_max = 0; fr.xxh_lo = 0; fr.lit_garbage = 0;
+    fr.fail_block = 0; fr.pad_ = 0;
+    fr.end_owner[0] = fr.end_owner[1] = fr.end_owner[2] = fr.end_owner[3] = KZG_INVALID_OWNER;
+    fr.end_rep[0] = 1; fr.end_rep[1] = 4; fr.end_rep[2] = 8;
     if (fsz >= 8 && (kzg_rd32(f) & 0xFFFFFFF0u) == KZG_SKIP_MAGIC) {     // skippable frame: no output
         if (8ull + kzg_rd32(f + 4) != fsz) fr.status = KZG_E_SRCSIZE_WRONG;
         B.frames[i] = fr;
@@ -48,6 +51,7 @@ KZG_HD void kzg_stage_scan(const KzgBatch& B, u32 i) {
     u32 block_max = 0;
     if (!err) {
         block_max = h.window_size < KZG_BLOCK_MAX ? (u32)h.window_size : KZG_BLOCK_MAX;
+        if (B.seg_mode) block_max = B.seg_block_max;
         pos = h.hdr_size;
         for (;;) {
             if (pos + 3 > fsz) { err = KZG_E_SRCSIZE_WRONG; break; }
@@ -131,6 +135,7 @@ KZG_HD void kzg_stage_link(const KzgBatch& B, u32 i) {
     // a formatted dictionary preloads the Huffman table and the three FSE tables of every frame
     const u32 start = B.dict_entropy ? KZG_DICT_OWNER : KZG_INVALID_OWNER;
     u32 huf_cur = start, fse_cur[3] = { start, start, start };
+    if (B.seg_mode) { huf_cur = B.init_owner[0]; fse_cur[0] = B.init_owner[1]; fse_cur[1] = B.init_owner[2]; fse_cur[2] = B.init_owner[3]; }
     u32 seen_seq = 0;
     for (u32 k = 0; k < fr.n_blocks; k++) {
         const u32 c = B.blocks[fr.first_block + k].cidx;
@@ -157,6 +162,8 @@ KZG_HD void kzg_stage_link(const KzgBatch& B, u32 i) {
             seen_seq = 1;
         }
     }
+    KzgFrame* fw = &B.frames[i];
+    fw->end_owner[0] = huf_cur; fw->end_owner[1] = fse_cur[0]; fw->end_owner[2] = fse_cur[1]; fw->end_owner[3] = fse_cur[2];
 }
 
 // huffman: decode stream `st` of Huffman block h (index into hlist) with the already built table
@@ -216,13 +223,14 @@ KZG_HD void kzg_stage_offsets(const KzgBatch& B, u32 i) {
     u32 err = KZG_OK;
     u32 rep[3] = { 1, 4, 8 };
     if (B.dict_entropy) { rep[0] = B.dict_rep[0]; rep[1] = B.dict_rep[1]; rep[2] = B.dict_rep[2]; }
-    for (u32 k = 0; k < fr->n_blocks; k++) {
+    u32 k = 0;
+    for (; k < fr->n_blocks; k++) {
         KzgBlock* blk = &B.blocks[fr->first_block + k];
         if (blk->type == 2) {
             KzgCBlock* cb = &B.cblocks[blk->cidx];
             err = cb->status_lit ? cb->status_lit : cb->status_seq;
             if (err) break;
-            if (cb->lit_garbage) fr->lit_garbage = 1u;
+            if (cb->lit_garbage && !fr->lit_garbage) { fr->lit_garbage = 1u; fr->fail_block = k; }
             u32 regen = cb->lit_regen;
             if (cb->n_seq > 0) {
                 regen = cb->regen;
@@ -238,10 +246,12 @@ KZG_HD void kzg_stage_offsets(const KzgBatch& B, u32 i) {
         pos += blk->regen;
         if (pos > cap) { err = KZG_E_DSTSIZE_TOO_SMALL; break; }
     }
-    if (!err && fr->fcs != ~0ull && pos != fr->fcs) err = KZG_E_CORRUPTION;
+    // (libzstd compares the content size when it decodes the last block: the blocks before it have been handed over)
+    if (!err && fr->fcs != ~0ull && pos != fr->fcs) { err = KZG_E_CORRUPTION; k = fr->n_blocks - 1; }
     fr->status = err;
     fr->out_size = err ? 0 : pos;
-    if (err) return;
+    if (err) { fr->fail_block = k; return; }
+    fr->end_rep[0] = rep[0]; fr->end_rep[1] = rep[1]; fr->end_rep[2] = rep[2];
     // work list of the bulk kernel: raw / RLE blocks, literal-only blocks, long literal tails and runs
     for (u32 k = 0; k < fr->n_blocks; k++) {
         const KzgBlock* blk = &B.blocks[fr->first_block + k];

@@ -28,6 +28,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <new>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -211,6 +212,29 @@ public:
         return true;
     }
 
+    // Runs f(ctx) with one device context to itself (segment decoding of one handle).
+    template <class F> int with_lane(F&& f) {
+        std::unique_lock<std::mutex> lk(mu_);
+        Lane* lane = nullptr;
+        for (;;) {
+            for (int i = 0; i < kLanes && !lane; i++) if (!lanes_[i].busy) lane = &lanes_[i];
+            if (lane) break;
+            cv_.wait(lk);
+        }
+        lane->busy = true;
+        lk.unlock();
+        int rc = 0;
+        if (!lane->ctx) {
+            kzg_ctx* c = nullptr;
+            if (kzg_ctx_create(&c, -1) == 0) lane->ctx = c; else rc = -(int)KZG_E_MEMORY;
+        }
+        if (rc == 0) rc = f(lane->ctx);
+        lk.lock();
+        lane->busy = false;
+        cv_.notify_all();
+        return rc;
+    }
+
     int submit(Req& r) {
         std::unique_lock<std::mutex> lk(mu_);
         if (!lanes_[0].ctx) return -(int)KZG_E_MEMORY;
@@ -271,24 +295,301 @@ Batcher g_batcher;
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ decompress side
+// The handle behaves like ZSTD_decompressStream, call for call (Wrapper.cpp:178; driven by SliceTransform.kt:33-45 and
+// SliceTransformRawSource.kt:32-55).  What a caller of libzstd can observe, and therefore what is restated here:
+//   * output leaves block by block; a call returns when the output slice is full, when the input runs dry (all of it has
+//     been taken over then), or -- with 0 -- when a frame has been handed over completely, and then the input is only
+//     consumed up to the end of that frame;
+//   * an error is returned by the call that reaches it, and that call hands over nothing (libzstd does not advance the
+//     positions on an error): what the caller keeps is what earlier calls delivered -- the frames in front of a bad one,
+//     and of the bad frame the blocks in front of the bad block as far as whole calls delivered them;
+//   * an incomplete frame is not an error: its complete blocks are decoded and handed over, the rest waits.
+// Underneath, decoding runs AHEAD of what has been handed over, in rounds, so that the GPU sees batches: a round takes
+// every complete frame at the parse position (up to kAhead bytes of output; one GPU batch through the cross-handle
+// batcher above), or -- for a frame that is not complete yet or larger than a segment -- the next run of complete
+// blocks of that frame (kzg_decompress_segment_host: entropy tables, repeat offsets, checksum and the last window
+// bytes of output carry over).  A round starts only when everything decoded so far has been handed over, so a handle
+// holds at most kAhead bytes of output plus the frame's window, whatever the size of the stream.
+struct Unit {                    // one step of the hand-over: a frame, a segment of one, or an error
+    size_t out_len = 0;          // bytes in the arena
+    uint64_t in_end = 0;         // stream offset consumed through this unit
+    bool frame_end = false;      // the call that finishes it returns 0
+    size_t error = 0;            // nonzero: no data; the call that reaches it returns this
+};
+
+struct SegFrame {                // the frame that is being decoded in segments
+    bool active = false, last_seen = false;      // last_seen: every block is decoded, only the checksum is missing
+    kzg_seg_state st;
+    uint64_t fcs = ~0ull, produced = 0, window = 0;
+    bool has_checksum = false;
+    std::vector<u8> hist;        // the last `window` bytes of content (in front of them: what is left of the dictionary)
+};
+
 struct kzg_DCtx {
-    std::vector<u8> in;          // compressed bytes of a frame that is not complete yet
-    Arena out;                   // decoded bytes not yet handed to the caller: out.p[out_pos, out_size)
-    size_t out_size = 0, out_pos = 0;
     std::vector<u8> dict;
+    uint64_t reported = 0;       // stream bytes the caller has been told are consumed
+    uint64_t engine = 0;         // stream bytes decoded (or skipped) so far; >= reported
+    std::vector<u8> own;         // stream bytes [engine, engine + own.size()) taken over from the caller
+    Arena out;                   // decoded bytes not yet handed over: out.p[out_pos, out_size)
+    size_t out_size = 0, out_pos = 0;
+    std::vector<Unit> units;     // hand-over queue, units[unit_head] is current
+    size_t unit_head = 0, cur_left = 0;
+    bool cur_open = false;       // cur_left is valid for units[unit_head]
+    SegFrame seg;
     std::vector<uint64_t> off, size, content, doff;
     std::vector<uint32_t> status;
     std::vector<uint64_t> osize;
     size_t sticky_error = 0;
-    size_t deferred_error = 0;   // error of a later frame of the same call: reported once the output of the frames before it is delivered
 };
 
-// Most output one call may hold (all frames completed by that call together); beyond it the call fails with
-// memory_allocation instead of reserving whatever a few bytes of RLE blocks can claim.  KZG_STREAM_MAX_OUT_MB overrides.
-static uint64_t stream_max_out() {
+namespace {
+
+const uint64_t kAhead = 64ull << 20;         // most output one round decodes ahead of the hand-over
+const uint64_t kSegMax = 32ull << 20;        // most output of one segment; frames above it are decoded in segments
+
+// Most output one handle may hold.  KZG_STREAM_MAX_OUT_MB overrides (tests).
+uint64_t stream_max_out() {
     static const uint64_t v = [] { const char* e = getenv("KZG_STREAM_MAX_OUT_MB"); const uint64_t m = e ? strtoull(e, nullptr, 10) : 0; return (m ? m : 4096ull) << 20; }();
     return v;
 }
+
+bool arena_reserve(kzg_DCtx* d, size_t extra) {          // room for `extra` more bytes behind out_size
+    if (d->out.cap >= d->out_size + extra + 64) return true;
+    Arena a = g_pool.acquire(d->out_size + extra + 64);
+    if (!a.p) return false;
+    if (d->out_size) memcpy(a.p, d->out.p, d->out_size);
+    g_pool.release(d->out);
+    d->out = a;
+    return true;
+}
+
+void push_unit(kzg_DCtx* d, size_t out_len, uint64_t in_end, bool frame_end, size_t error) {
+    Unit u; u.out_len = out_len; u.in_end = in_end; u.frame_end = frame_end; u.error = error;
+    d->units.push_back(u);
+}
+
+// Walks whole blocks in [v, v + n): how many, where the last header is, their output bound.  Stops at the last block of
+// the frame, at an incomplete block, at `max_blocks`, or when the bound would exceed `max_out` (never before one block).
+struct BlockRun { size_t bytes = 0, last_hdr = 0, count = 0; uint64_t bound = 0; bool last = false; u32 error = 0; };
+BlockRun walk_blocks(const u8* v, size_t n, u32 block_max, uint64_t max_out, size_t max_blocks) {
+    BlockRun r;
+    size_t q = 0;
+    while (q + 3 <= n && r.count < max_blocks) {
+        const u32 bh = kzg_rd24(v + q);
+        const u32 type = (bh >> 1) & 3, bsz = bh >> 3;
+        if (type == 3 || bsz > block_max) { r.error = KZG_E_CORRUPTION; break; }
+        const size_t adv = type == 1 ? 1 : bsz;
+        if (q + 3 + adv > n) break;
+        const uint64_t add = type == 2 ? block_max : bsz;
+        if (r.count && r.bound + add > max_out) break;
+        r.bound += add; r.last_hdr = q; r.count++;
+        q += 3 + adv;
+        r.bytes = q;
+        if (bh & 1) { r.last = true; break; }
+    }
+    return r;
+}
+
+// One segment of the active frame, decoded behind out_size.  Returns 0 or an error value; *osize / *status as the batch calls.
+size_t run_segment(kzg_DCtx* d, const u8* blocks, const BlockRun& r, uint32_t* status, uint64_t* osize) {
+    if (!arena_reserve(d, (size_t)r.bound)) return err(KZG_E_MEMORY);
+    u8* dst = d->out.p + d->out_size;
+    SegFrame& sg = d->seg;
+    const int rc = g_batcher.with_lane([&](kzg_ctx* ctx) {
+        return kzg_decompress_segment_host(ctx, &sg.st, blocks, r.bytes, r.last_hdr, sg.hist.data(), sg.hist.size(), dst, (size_t)r.bound + 32, status, osize);
+    });
+    if (rc < 0) return err((u32)(-rc));
+    return 0;
+}
+
+void seg_commit(kzg_DCtx* d, uint64_t n) {                // n bytes behind out_size are content of the active frame
+    SegFrame& sg = d->seg;
+    const u8* p = d->out.p + d->out_size;
+    if (n >= sg.window) sg.hist.assign(p + (n - sg.window), p + n);
+    else {
+        sg.hist.insert(sg.hist.end(), p, p + n);
+        if (sg.hist.size() > sg.window) sg.hist.erase(sg.hist.begin(), sg.hist.begin() + (sg.hist.size() - (size_t)sg.window));
+    }
+    sg.produced += n;
+    d->out_size += (size_t)n;
+}
+
+// The blocks [0, k) of a run decoded on their own (what libzstd has handed over before it meets the bad block k), from
+// the state `st0` the run started with.  Queues them as one unit.
+void queue_good_prefix(kzg_DCtx* d, const u8* blocks, size_t n, u32 block_max, size_t k, const kzg_seg_state& st0, uint64_t in_end_base) {
+    if (k == 0) return;
+    d->seg.st = st0;
+    const BlockRun r = walk_blocks(blocks, n, block_max, ~0ull, k);
+    if (r.count != k || r.error) return;
+    uint32_t st = 0; uint64_t os = 0;
+    if (run_segment(d, blocks, r, &st, &os) != 0 || st != 0) return;
+    seg_commit(d, os);
+    push_unit(d, (size_t)os, in_end_base + r.bytes, false, 0);
+}
+
+// Segment mode: the next run of whole blocks of the active frame (or its checksum).  Returns the stream bytes taken.
+size_t seg_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
+    SegFrame& sg = d->seg;
+    if (sg.last_seen) {
+        if (n < 4) { *incomplete = true; return 0; }
+        const bool ok = kzg_rd32(v) == kzg_segment_checksum(&sg.st);
+        sg.active = false;
+        if (ok) push_unit(d, 0, d->engine + 4, true, 0);
+        else push_unit(d, 0, d->engine, false, err(KZG_E_CHECKSUM_WRONG));
+        return ok ? 4 : 0;
+    }
+    BlockRun r = walk_blocks(v, n, sg.st.block_max, kSegMax, ~(size_t)0);
+    // libzstd compares the content size when it decodes the last block, before handing it over: that block goes alone
+    if (r.last && r.count > 1 && sg.fcs != ~0ull) r = walk_blocks(v, n, sg.st.block_max, kSegMax, r.count - 1);
+    if (r.count == 0) {
+        if (r.error) { sg.active = false; push_unit(d, 0, d->engine, false, err(r.error)); return 0; }
+        *incomplete = true;
+        return 0;
+    }
+    const kzg_seg_state st0 = sg.st;
+    const std::vector<u8> hist0 = sg.hist;         // (a failed run is decoded again up to the bad block)
+    uint32_t st = 0; uint64_t os = 0;
+    const size_t e = run_segment(d, v, r, &st, &os);
+    if (getenv("KZG_STREAM_DEBUG")) fprintf(stderr, "seg_round: engine %llu n %zu blocks %zu bytes %zu bound %llu last %d -> rc %zd status %u osize %llu hist %zu\n",
+                                            (unsigned long long)d->engine, n, r.count, r.bytes, (unsigned long long)r.bound, (int)r.last, (ssize_t)e, st, (unsigned long long)os, sg.hist.size());
+    if (e) { sg.active = false; push_unit(d, 0, d->engine, false, e); return 0; }
+    if (st == 0 && r.last && sg.fcs != ~0ull && sg.produced + os != sg.fcs) { st = KZG_E_CORRUPTION; os = 0; }
+    if (st != 0) {
+        sg.hist = hist0;
+        queue_good_prefix(d, v, n, st0.block_max, (size_t)(os & 0x7FFFFFFFull), st0, d->engine);
+        sg.active = false;
+        push_unit(d, 0, d->engine, false, err(st));
+        return 0;
+    }
+    seg_commit(d, os);
+    const bool ends = r.last && !sg.has_checksum;
+    push_unit(d, (size_t)os, d->engine + r.bytes, ends, 0);
+    if (r.last) { if (sg.has_checksum) sg.last_seen = true; else sg.active = false; }
+    return r.bytes;
+}
+
+// Starts segment mode for the frame at v (its header is complete).  Returns the header bytes taken, 0 with a queued error.
+size_t seg_start(kzg_DCtx* d, const KzgFrameHeader& h) {
+    SegFrame& sg = d->seg;
+    u32 dict_id = 0;
+    if (d->dict.size() >= 8 && kzg_rd32(d->dict.data()) == KZG_DICT_MAGIC) dict_id = kzg_rd32(d->dict.data() + 4);
+    if (h.dict_id && h.dict_id != dict_id) { push_unit(d, 0, d->engine, false, err(KZG_E_DICT_WRONG)); return 0; }
+    const u32 block_max = h.window_size < KZG_BLOCK_MAX ? (u32)h.window_size : KZG_BLOCK_MAX;
+    const long long content = kzg_segment_begin(&sg.st, block_max, (int)h.has_checksum, d->dict.empty() ? nullptr : d->dict.data(), d->dict.size());
+    if (content < 0) { push_unit(d, 0, d->engine, false, err((u32)(-content))); return 0; }
+    sg.active = true; sg.last_seen = false;
+    sg.fcs = h.fcs; sg.produced = 0; sg.window = h.window_size; sg.has_checksum = h.has_checksum != 0;
+    sg.hist.assign(d->dict.end() - (size_t)content, d->dict.end());
+    return h.hdr_size;
+}
+
+// One round of decoding at the parse position: v[0, n) are the stream bytes from d->engine on.  Queues units; returns the
+// stream bytes taken.  *incomplete: nothing could be done because the next block / frame is not complete.
+size_t engine_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
+    *incomplete = false;
+    if (d->seg.active) return seg_round(d, v, n, incomplete);
+    // ---- at a frame start: every complete frame from here on, as one batch
+    size_t pos = 0, nf = 0;
+    uint64_t total = 0;
+    d->off.clear(); d->size.clear(); d->content.clear();
+    size_t stop_error = 0;
+    bool start_segments = false;
+    KzgFrameHeader seg_h;
+    while (pos < n) {
+        const u8* f = v + pos;
+        const size_t rem = n - pos;
+        if (rem < 4) break;
+        const u32 magic = kzg_rd32(f);
+        if ((magic & 0xFFFFFFF0u) == KZG_SKIP_MAGIC) {
+            if (rem < 8 || 8ull + kzg_rd32(f + 4) > rem) break;
+            d->off.push_back(pos); d->size.push_back(8ull + kzg_rd32(f + 4)); d->content.push_back(0);
+            pos += (size_t)d->size.back(); nf++;
+            continue;
+        }
+        KzgFrameHeader h;
+        const u32 e = magic != KZG_MAGIC ? (u32)KZG_E_PREFIX_UNKNOWN : kzg_parse_frame_header(f, rem, h);
+        if (e == KZG_E_SRCSIZE_WRONG) break;
+        if (e) { stop_error = err(e); break; }
+        // ZSTD_decompressStream refuses frames whose window exceeds ZSTD_WINDOWLOG_LIMIT_DEFAULT (2^27) (SURVEY.md
+        // Appendix C: windowLog 28 -> -16); through Kompressor's small output slices that also holds for single-segment frames
+        if (h.window_size > (1ull << 27) + 1) { stop_error = err(KZG_E_WINDOW_TOO_LARGE); break; }
+        const u32 block_max = h.window_size < KZG_BLOCK_MAX ? (u32)h.window_size : KZG_BLOCK_MAX;
+        const BlockRun r = walk_blocks(f + h.hdr_size, rem - h.hdr_size, block_max, ~0ull, ~(size_t)0);
+        const size_t fsz = h.hdr_size + r.bytes + (h.has_checksum ? 4 : 0);
+        const bool complete = r.last && !r.error && fsz <= rem;
+        if (!complete || r.bound > kSegMax) {
+            // not complete yet, broken block structure, or too large for one piece: block by block
+            if (nf == 0) { start_segments = true; seg_h = h; }
+            break;
+        }
+        // (the Frame_Content_Size field is untrusted: a frame cannot regenerate more than its blocks allow)
+        const uint64_t cap = (h.fcs != ~0ull && h.fcs < r.bound) ? h.fcs : r.bound;
+        if (nf && total + cap > kAhead) break;
+        d->off.push_back(pos); d->size.push_back(fsz); d->content.push_back(cap);
+        total += (cap + 15) & ~15ull;
+        pos += fsz; nf++;
+    }
+    if (nf == 0) {
+        if (start_segments) return seg_start(d, seg_h);
+        if (stop_error) { push_unit(d, 0, d->engine, false, stop_error); return 0; }
+        *incomplete = true;
+        return 0;
+    }
+    if (total > stream_max_out()) { push_unit(d, 0, d->engine, false, err(KZG_E_MEMORY)); return 0; }
+    try { d->doff.resize(nf); d->status.resize(nf); d->osize.resize(nf); } catch (const std::bad_alloc&) { push_unit(d, 0, d->engine, false, err(KZG_E_MEMORY)); return 0; }
+    uint64_t t = 0, src_total = 0;
+    for (size_t i = 0; i < nf; i++) { d->doff[i] = t; t += (d->content[i] + 15) & ~15ull; src_total += d->size[i]; }
+    if (!arena_reserve(d, (size_t)total)) { push_unit(d, 0, d->engine, false, err(KZG_E_MEMORY)); return 0; }
+    const size_t base = d->out_size;
+    Req rq;
+    rq.src = v; rq.off = d->off.data(); rq.size = d->size.data(); rq.content = d->content.data(); rq.doff = d->doff.data();
+    rq.n = nf; rq.src_bytes = src_total; rq.dst_bytes = total;
+    rq.dst = d->out.p + base; rq.status = d->status.data(); rq.osize = d->osize.data(); rq.dict = &d->dict;
+    const int rc = g_batcher.submit(rq);
+    if (rc < 0) { push_unit(d, 0, d->engine, false, err((u32)(-rc))); return 0; }
+    // compact the outputs (frames were decoded at capacity-spaced offsets) and queue them
+    size_t w = base, taken = 0;
+    for (size_t i = 0; i < nf; i++) {
+        const uint64_t in_end = d->engine + d->off[i] + d->size[i];
+        if (d->status[i] == 0 || (d->status[i] == KZG_E_CHECKSUM_WRONG && !(d->osize[i] >> 63) && d->osize[i] <= d->content[i])) {
+            if (w != base + d->doff[i]) memmove(d->out.p + w, d->out.p + base + d->doff[i], (size_t)d->osize[i]);
+            w += (size_t)d->osize[i];
+            d->out_size = w;
+            if (d->status[i]) {      // the content is all there, the checksum does not match it: handed over, then the error
+                push_unit(d, (size_t)d->osize[i], d->engine + d->off[i], false, 0);
+                push_unit(d, 0, d->engine + d->off[i], false, err(d->status[i]));
+                return taken;
+            }
+            push_unit(d, (size_t)d->osize[i], in_end, true, 0);
+            taken = (size_t)(d->off[i] + d->size[i]);
+            continue;
+        }
+        // a bad frame: what libzstd hands over first are the blocks in front of the bad one (out_size names it)
+        d->out_size = w;
+        const u8* f = v + d->off[i];
+        KzgFrameHeader h;
+        const size_t bad_block = (size_t)(d->osize[i] & 0x7FFFFFFFull);
+        if ((kzg_rd32(f) & 0xFFFFFFF0u) != KZG_SKIP_MAGIC && kzg_parse_frame_header(f, (size_t)d->size[i], h) == KZG_OK && bad_block > 0 &&
+            d->status[i] != KZG_E_DICT_WRONG) {
+            d->engine += d->off[i];                          // (seg_start / the prefix units count from the frame's start)
+            const size_t hs = seg_start(d, h);
+            if (hs) {
+                const kzg_seg_state st0 = d->seg.st;
+                d->engine += hs;
+                queue_good_prefix(d, f + hs, (size_t)d->size[i] - hs, st0.block_max, bad_block, st0, d->engine);
+                d->engine -= hs;
+            }
+            d->seg.active = false;
+            d->engine -= d->off[i];
+        }
+        push_unit(d, 0, d->engine + d->off[i], false, err(d->status[i]));
+        return taken;
+    }
+    return taken;
+}
+
+}  // namespace
 
 extern "C" kzg_DCtx* kzg_createDCtx(void) {
     if (!g_batcher.ready()) return nullptr;       // no GPU: no decoder (there is no CPU fallback)
@@ -303,120 +604,83 @@ extern "C" size_t kzg_freeDCtx(kzg_DCtx* d) {
 
 extern "C" size_t kzg_DCtx_loadDictionary(kzg_DCtx* d, const void* dict, size_t n) {
     if (!d) return err(KZG_E_GENERIC);
-    if (!d->in.empty() || d->out_pos < d->out_size) return err(60 /* stage_wrong */);
+    if (d->engine != d->reported || !d->own.empty() || d->unit_head < d->units.size() || d->seg.active) return err(60 /* stage_wrong */);
     d->dict.assign((const u8*)dict, (const u8*)dict + (dict ? n : 0));
     return 0;
-}
-
-// Decodes the complete frames in [p, p+len); appends output to d->out. Returns bytes consumed or error.
-static size_t decode_complete_frames(kzg_DCtx* d, const u8* p, size_t len, size_t* n_frames_out) {
-    *n_frames_out = 0;
-    size_t consumed = 0;
-    const size_t cap = kzg_scan_frames(p, len, nullptr, nullptr, nullptr, (size_t)-1, &consumed);     // count, then fill
-    if (kzg_isError(cap)) return cap;
-    if (cap == 0) return 0;
-    try { d->off.resize(cap); d->size.resize(cap); d->content.resize(cap); } catch (const std::bad_alloc&) { return err(KZG_E_MEMORY); }
-    const size_t n = kzg_scan_frames(p, len, d->off.data(), d->size.data(), d->content.data(), cap, &consumed);
-    if (kzg_isError(n)) return n;
-    if (n == 0) return 0;
-    try { d->doff.resize(n); d->status.resize(n); d->osize.resize(n); } catch (const std::bad_alloc&) { return err(KZG_E_MEMORY); }
-    // ZSTD_decompressStream refuses frames whose window exceeds ZSTD_WINDOWLOG_LIMIT_DEFAULT (2^27)
-    // (windowLog 28 -> -16); through Kompressor's small output slices that
-    // also holds for single-segment frames.
-    for (size_t i = 0; i < n; i++) {
-        KzgFrameHeader h;
-        if (d->size[i] >= 5 && kzg_rd32(p + d->off[i]) == KZG_MAGIC &&
-            kzg_parse_frame_header(p + d->off[i], d->size[i], h) == KZG_OK && h.window_size > (1ull << 27) + 1)
-            return err(KZG_E_WINDOW_TOO_LARGE);
-    }
-    uint64_t total = 0, src_total = 0;
-    for (size_t i = 0; i < n; i++) {
-        // (content[i] is bounded by what the frame's blocks can regenerate, see kzg_scan_frames: no sum here can wrap)
-        d->doff[i] = total; total += (d->content[i] + 15) & ~15ull; src_total += d->size[i];
-        if (total > stream_max_out()) return err(KZG_E_MEMORY);
-    }
-    // output arena: what is still pending moves to the front of a buffer that also holds the new frames
-    const size_t pending = d->out_size - d->out_pos;
-    if (pending == 0) { d->out_pos = d->out_size = 0; }
-    if (d->out.cap < pending + total + 64 || d->out_pos) {
-        if (d->out.cap >= pending + total + 64) {
-            memmove(d->out.p, d->out.p + d->out_pos, pending);
-        } else {
-            Arena a = g_pool.acquire(pending + total + 64);
-            if (!a.p) return err(KZG_E_MEMORY);
-            if (pending) memcpy(a.p, d->out.p + d->out_pos, pending);
-            g_pool.release(d->out);
-            d->out = a;
-        }
-        d->out_pos = 0;
-        d->out_size = pending;
-    }
-    const size_t base = d->out_size;
-    Req r;
-    r.src = p; r.off = d->off.data(); r.size = d->size.data(); r.content = d->content.data(); r.doff = d->doff.data();
-    r.n = n; r.src_bytes = src_total; r.dst_bytes = total;
-    r.dst = d->out.p + base; r.status = d->status.data(); r.osize = d->osize.data(); r.dict = &d->dict;
-    const int rc = g_batcher.submit(r);
-    if (rc < 0) return err((u32)(-rc));
-    // compact the outputs (frames were decoded at capacity-spaced offsets)
-    size_t w = base;
-    for (size_t i = 0; i < n; i++) {
-        if (d->status[i]) {
-            // libzstd has delivered the frames in front of a bad one by the time it reports the error: keep their
-            // output and report the error when it has been handed over
-            d->out_size = w;
-            *n_frames_out = i;
-            if (w == base && d->out_pos == d->out_size) return err(d->status[i]);
-            d->deferred_error = err(d->status[i]);
-            return consumed;
-        }
-        if (w != base + d->doff[i]) memmove(d->out.p + w, d->out.p + base + d->doff[i], d->osize[i]);
-        w += d->osize[i];
-    }
-    d->out_size = w;
-    *n_frames_out = n;
-    return consumed;
 }
 
 extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_inBuffer* input) {
     if (!d || !output || !input) return err(KZG_E_GENERIC);
     if (input->pos > input->size || output->pos > output->size) return err(KZG_E_SRCSIZE_WRONG);
     if (d->sticky_error) return d->sticky_error;
-    const u8* src = (const u8*)input->src + input->pos;
+    const u8* src = (const u8*)input->src + input->pos;           // stream offset d->reported
     const size_t avail = input->size - input->pos;
-    size_t frames_done = 0;
-    if (avail || !d->in.empty()) {
-        size_t used;
-        if (d->in.empty()) {                      // fast path: decode straight from the caller's buffer
-            used = decode_complete_frames(d, src, avail, &frames_done);
-            if (kzg_isError(used)) { d->sticky_error = used; return used; }
-            d->in.assign(src + used, src + avail);
+    const size_t out_entry = output->pos;
+    const uint64_t rep_entry = d->reported;                       // stream offset of src[0]
+    // bytes of this call the handle has not seen yet: those behind what it decoded ahead or took over earlier
+    const uint64_t seen_end = d->engine + d->own.size();
+    size_t fresh_lo = seen_end > rep_entry ? (size_t)(seen_end - rep_entry) : 0;
+    if (fresh_lo > avail) fresh_lo = avail;                       // (a caller that presents less than before: nothing new)
+    bool waiting = false;                                         // the next block / frame is not complete
+    size_t result = 0;
+    for (;;) {
+        // ---- hand over
+        if (d->unit_head < d->units.size()) {
+            Unit& u = d->units[d->unit_head];
+            if (u.error) {                                        // libzstd: positions do not advance on an error
+                output->pos = out_entry;
+                d->sticky_error = u.error;
+                return u.error;
+            }
+            if (!d->cur_open) { d->cur_open = true; d->cur_left = u.out_len; }
+            const size_t room = output->size - output->pos;
+            const size_t k = d->cur_left < room ? d->cur_left : room;
+            if (k) memcpy((u8*)output->dst + output->pos, d->out.p + d->out_pos, k);
+            output->pos += k; d->out_pos += k; d->cur_left -= k;
+            if (d->cur_left) { result = d->cur_left; break; }     // the slice is full in the middle of a block run
+            const bool fe = u.frame_end;
+            const uint64_t in_end = u.in_end;
+            d->cur_open = false;
+            d->unit_head++;
+            if (d->unit_head == d->units.size()) {                // everything decoded so far is handed over
+                d->units.clear(); d->unit_head = 0;
+                d->out_pos = d->out_size = 0;
+                if (d->out.cap > (1u << 20)) g_pool.release(d->out);      // large arenas go back to the pool at once
+            }
+            if (in_end > d->reported) { input->pos += (size_t)(in_end - d->reported); d->reported = in_end; }
+            if (fe) { result = 0; goto done; }                     // a frame boundary: libzstd returns 0 and stops consuming
+            continue;
+        }
+        // ---- decode ahead: one round at the parse position
+        const u8* v; size_t n;
+        if (d->own.empty()) {
+            const size_t skip = (size_t)(d->engine - rep_entry);
+            v = src + skip; n = avail > skip ? avail - skip : 0;
         } else {
-            d->in.insert(d->in.end(), src, src + avail);
-            used = decode_complete_frames(d, d->in.data(), d->in.size(), &frames_done);
-            if (kzg_isError(used)) { d->sticky_error = used; return used; }
-            d->in.erase(d->in.begin(), d->in.begin() + used);
+            if (fresh_lo < avail) { d->own.insert(d->own.end(), src + fresh_lo, src + avail); fresh_lo = avail; }
+            v = d->own.data(); n = d->own.size();
         }
-        input->pos = input->size;                 // zstd never leaves input behind (input.insufficient is never set)
+        bool incomplete = false;
+        const size_t took = n ? engine_round(d, v, n, &incomplete) : 0;
+        if (!n) incomplete = true;
+        d->engine += took;
+        if (!d->own.empty()) d->own.erase(d->own.begin(), d->own.begin() + took);
+        if (d->unit_head < d->units.size() || took) continue;
+        (void)incomplete;
+        // nothing more can be decoded: libzstd has taken all the input into its own buffer by now
+        if (d->own.empty() && n) d->own.assign(v, v + n);
+        waiting = true;
+        break;
     }
-    size_t delivered = 0;
-    {
-        const size_t have = d->out_size - d->out_pos, room = output->size - output->pos;
-        delivered = have < room ? have : room;
-        if (delivered) memcpy((u8*)output->dst + output->pos, d->out.p + d->out_pos, delivered);
-        output->pos += delivered;
-        d->out_pos += delivered;
-        if (d->out_pos == d->out_size) {
-            d->out_pos = d->out_size = 0;
-            if (d->out.cap > (1u << 20)) g_pool.release(d->out);      // large arenas go back to the pool at once
-        }
+    if (waiting) {
+        const uint64_t all = rep_entry + avail;
+        input->pos = input->size;
+        d->reported = all;
+        // hint: inside a frame, or idle at a frame start (libzstd: header + block header)
+        result = (d->seg.active || !d->own.empty()) ? (d->own.size() < 9 ? 9 - d->own.size() : 3) : 9;
     }
-    const size_t pending = d->out_size - d->out_pos;
-    if (pending) return pending;                          // undelivered output: caller must come back with room
-    if (d->deferred_error) { d->sticky_error = d->deferred_error; d->in.clear(); return d->sticky_error; }
-    if (!d->in.empty()) return d->in.size() < 9 ? 9 - d->in.size() : 3;   // inside a frame: hint for more input
-    if (frames_done || delivered) return 0;               // frame boundary, everything flushed
-    return 9;                                             // idle at a frame start (libzstd: header + block header hint)
+done:
+    return result;
 }
 
 // ------------------------------------------------------------------------------------------------
