@@ -519,8 +519,10 @@ size_t engine_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
         const size_t fsz = h.hdr_size + r.bytes + (h.has_checksum ? 4 : 0);
         const bool complete = r.last && !r.error && fsz <= rem;
         if (!complete || r.bound > kSegMax) {
-            // not complete yet, broken block structure, or too large for one piece: block by block
-            if (nf == 0) { start_segments = true; seg_h = h; }
+            // Not complete yet, broken block structure, or too large for one piece: block by block -- but only when a
+            // whole block is there to hand over.  A frame whose first block is still arriving just waits: once it is
+            // complete it goes through the batch path, where the calls of many handles are merged into one GPU batch.
+            if (nf == 0 && (r.count || r.error)) { start_segments = true; seg_h = h; }
             break;
         }
         // (the Frame_Content_Size field is untrusted: a frame cannot regenerate more than its blocks allow)

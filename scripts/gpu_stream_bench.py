@@ -68,7 +68,8 @@ def run_stream(comp: np.ndarray, raw_len: int, in_slice: int, out_slice: int, ou
             r = L.kzg_decompressStream(d, ctypes.byref(outb), ctypes.byref(inb))
             assert not L.kzg_isError(r), L.kzg_getErrorName(r)
             op += outb.pos
-            if not (outb.pos == room and r != 0):      # output.insufficient = output.isFull && result != 0
+            # SliceTransform.kt:39-45: while (input.remainingRead != 0 || output.insufficient), insufficient = isFull && result != 0
+            if not (inb.pos < inb.size or (outb.pos == room and r != 0)):
                 break
         ip += take
         if ip >= n:

@@ -31,7 +31,8 @@ static Result run_stream(const uint8_t* comp, size_t n, size_t in_slice, size_t 
     while (ip < n) {
         const size_t take = in_slice == 0 ? n - ip : (in_slice < n - ip ? in_slice : n - ip);
         kzg_inBuffer ib = { comp + ip, take, 0 };
-        for (;;) {
+        bool insufficient = false;
+        do {                                                 // SliceTransform.kt:39-45: while (input.remainingRead != 0 || output.insufficient)
             const size_t room = out_slice < out_cap - op ? out_slice : out_cap - op;
             kzg_outBuffer ob = { out + op, room, 0 };
             const auto t0 = clk::now();
@@ -39,8 +40,8 @@ static Result run_stream(const uint8_t* comp, size_t n, size_t in_slice, size_t 
             if (first) { r.first_ms = ms_since(t0); first = false; }
             if (kzg_isError(res)) { fprintf(stderr, "error: %s\n", kzg_getErrorName(res)); r.ok = false; kzg_freeDCtx(d); return r; }
             op += ob.pos;
-            if (!(ob.pos == room && res != 0)) break;        // output.insufficient = output.isFull && result != 0
-        }
+            insufficient = ob.pos == room && res != 0;       // output.insufficient = output.isFull && result != 0
+        } while (ib.pos < ib.size || insufficient);
         ip += take;
     }
     kzg_freeDCtx(d);
