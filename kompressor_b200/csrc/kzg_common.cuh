@@ -177,6 +177,7 @@ struct KzgBatch {
     u32 seg_mode;
     u32 init_owner[4];
     u32 seg_block_max;
+    u32 huf_long_min;   // blocks with at least this many Huffman-coded literals go to the full-table launch (set at launch)
     // workspace
     KzgFrame* frames;
     KzgBlock* blocks;

@@ -24,6 +24,9 @@
 // (kompressor-zstd--nativelib/src/jvmCommonMain/jni/Wrapper.cpp:178).
 #pragma once
 #include "kzg_exec.cuh"
+#ifdef KZG_X4_TIMING
+#include <stdio.h>
+#endif
 
 #define KZG_X4_WARPS 16
 #define KZG_X4_THREADS (KZG_X4_WARPS * 32)
@@ -60,6 +63,41 @@ __device__ __forceinline__ void warp_copy_hist(u32 d, u32 n, const u8* out, i32 
     }
 }
 
+// One lane fills n bytes at shared address d with the period of p (1..7) bytes that ends right in front of d (an
+// overlapping match with a short distance).  The period is read once; every output word is a byte permutation of it, so
+// nothing waits on the lane's own stores (byte by byte, every load would wait for the store before it).
+__device__ __forceinline__ void lane_fill_period(u32 d, u32 n, u32 p) {
+    if (n == 0) return;
+    const u32 sa = d - p, A = sa & ~3u, r = (sa & 3u) << 3;
+    const u32 w0 = lds32(A), w1 = lds32(A + 4), w2 = lds32(A + 8);
+    const u32 s0 = __funnelshift_r(w0, w1, r), s1 = __funnelshift_r(w1, w2, r);     // bytes sa .. sa + 7; the first p are the period
+    u32 m = 0;                                      // position inside the period of the next output byte
+    auto next4 = [&]() -> u32 {                     // the next four output bytes
+        u32 sel = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { sel |= m << (4 * j); m = m + 1 == p ? 0u : m + 1; }
+        return __byte_perm(s0, s1, sel);
+    };
+    const u32 h = min(n, (0u - d) & 3u);
+    if (h) {
+        const u32 save = m;
+        const u32 v = next4();
+        sts8(d, v);
+        if (h > 1) sts8(d + 1, v >> 8);
+        if (h > 2) sts8(d + 2, v >> 16);
+        m = save + h; while (m >= p) m -= p;
+        d += h; n -= h;
+    }
+    for (u32 rem = n >> 2; rem; rem--) { sts32(d, next4()); d += 4; }
+    const u32 t = n & 3u;
+    if (t) {
+        const u32 v = next4();
+        sts8(d, v);
+        if (t > 1) sts8(d + 1, v >> 8);
+        if (t > 2) sts8(d + 2, v >> 16);
+    }
+}
+
 }  // namespace kzg_x4
 
 // Executes one compressed block with sequences into the shared-memory window and flushes it.  Returns (uniformly over
@@ -85,7 +123,13 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
     volatile u32* oend = reinterpret_cast<volatile u32*>(__cvta_shared_to_generic(smem + KZG_X4_WIN + KZG_X4_LIT_BYTES + KZG_X4_MISC + KZG_X4_THREADS * KZG_X4_MSTAGE));
 
     u64 rec_n = tid < nseq ? __ldg(seqs + tid) : 0ull, prev_n = (tid && tid < nseq) ? __ldg(seqs + tid - 1) : 0ull;         // the step's records are fetched one step ahead
+#ifdef KZG_X4_TIMING
+    long long tA = 0, tB = 0, tC = 0, tD = 0; u32 nsteps = 0; long long tripsum = 0;
+#endif
     for (u32 sb0 = 0; sb0 < nseq; sb0 += KZG_X4_THREADS) {
+#ifdef KZG_X4_TIMING
+        const long long c0 = clock64();
+#endif
         const u32 i = sb0 + tid;
         const bool valid = i < nseq;
         const u64 rec = rec_n, prev = prev_n;
@@ -193,6 +237,13 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
             jb = min(lo, tid - 1u);                                     // (tid >= 1 here: sequence 0 of a step has no producer in it)
             if (tid == 0 || ja > jb) { ja = 1; jb = 0; }                // no producers: the source is literals of this very sequence
         }
+        // the words of completed lanes that hold the producers' bits, and the bits
+        const u32 w0 = ja >> 5, w1 = jb >> 5;
+        const u32 mask0 = ja > jb ? 0u : ((0xFFFFFFFFu << (ja & 31u)) & (w1 == w0 ? 0xFFFFFFFFu >> (31u - (jb & 31u)) : 0xFFFFFFFFu));
+        const u32 mask1 = 0xFFFFFFFFu >> (31u - (jb & 31u));
+#ifdef KZG_X4_TIMING
+        const long long c1 = clock64();
+#endif
         u32 donem = 0;                          // completed lanes of this warp (what misc[warp] holds)
         u32 trips = 0;
         bool go = early;                        // first trip: the matches whose sources are final already
@@ -201,8 +252,10 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
             const u32 gm = __ballot_sync(0xFFFFFFFFu, go);
             if (gm) {
                 const bool fast = inwin && off >= 8u && ml < KZG_X4_COOP;
+                const bool period = inwin && off < 8u && ml < KZG_X4_COOP;
                 lane_copy(win + mdst, (go && fast) ? ml : 0u, win + (u32)spos, false, 0u);
-                if (go && !fast && ml < KZG_X4_COOP) {       // short period, or a source reaching back before the block: bytes in order
+                if (__any_sync(0xFFFFFFFFu, go && period)) lane_fill_period(win + mdst, (go && period) ? ml : 0u, off);
+                if (go && !fast && !period && ml < KZG_X4_COOP) {       // a source reaching back before the block: bytes in order
                     for (u32 k = 0; k < ml; k++) {
                         const i32 p = spos + (i32)k;
                         u32 v;
@@ -240,26 +293,36 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
             pending = pending && !go;
             const u32 nowdone = __ballot_sync(0xFFFFFFFFu, fin);
             if (nowdone != donem) {
-                __threadfence_block();
+                asm volatile("fence.acq_rel.cta;" ::: "memory");
                 if (lane == 0) misc[warp] = nowdone;
                 donem = nowdone;
             }
             if (nowdone == 0xFFFFFFFFu) break;
-            if (++trips > (1u << 22)) { if (lane == 0) misc[35] = 1u; break; }      // cannot happen; never spin forever on a GPU
-            if (!gm) __nanosleep(40);           // nothing went: this warp only polls, leave the issue slots to the others
-            go = false;
-            if (pending) {
-                bool ok = true;
-                for (u32 w = ja >> 5; w <= (jb >> 5) && ok; w++) {
-                    const u32 lo_b = w == (ja >> 5) ? (ja & 31u) : 0u, hi_b = w == (jb >> 5) ? (jb & 31u) : 31u;
-                    const u32 mask = (0xFFFFFFFFu >> (31u - hi_b)) & (0xFFFFFFFFu << lo_b);
-                    const u32 dw = w == warp ? nowdone : misc[w];
-                    ok = (dw & mask) == mask;
+            // poll until a lane of this warp can go (its producers' bits are set; a producer in this very warp counts at once)
+            for (;;) {
+                go = false;
+                if (pending) {
+                    const u32 d0 = w0 == warp ? nowdone : misc[w0];
+                    bool ok = (d0 & mask0) == mask0;
+                    if (w1 != w0) {
+                        const u32 d1 = w1 == warp ? nowdone : misc[w1];
+                        ok = ok && (d1 & mask1) == mask1;
+                        for (u32 w = w0 + 1; w < w1 && ok; w++) ok = (w == warp ? nowdone : misc[w]) == 0xFFFFFFFFu;
+                    }
+                    go = ok;
                 }
-                go = ok && ja <= jb || ja > jb;
+                if (__any_sync(0xFFFFFFFFu, go)) break;
+                if (++trips > (1u << 24)) { if (lane == 0) misc[35] = 1u; break; }      // cannot happen; never spin forever on a GPU
             }
+            if (trips > (1u << 24)) break;
         }
+#ifdef KZG_X4_TIMING
+        const long long c2 = clock64();
+#endif
         __syncthreads();                        // the step is complete: the next one may read all of it
+#ifdef KZG_X4_TIMING
+        { const long long c3 = clock64(); tA += c1 - c0; tB += c2 - c1; tC += c3 - c2; nsteps++; tripsum += trips; }
+#endif
         if (misc[35]) return 1u;
     }
     // ---- the literals after the last sequence, then the whole block leaves
@@ -280,6 +343,10 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
     }
     __threadfence();                    // later blocks read this one back from L2
     __syncthreads();
+#ifdef KZG_X4_TIMING
+    if (blockIdx.x == 0 && (tid & 31) == 0 && blk.out_off < (1u << 20)) printf("x4 warp %u: steps %u  phaseA %lld  chains %lld  barrier %lld  trips %lld (per step: %lld %lld %lld)\n", tid >> 5, nsteps, tA, tB, tC, tripsum, tA / nsteps, tB / nsteps, tC / nsteps);
+    (void)tD;
+#endif
     return 0u;
 }
 

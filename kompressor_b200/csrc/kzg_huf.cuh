@@ -78,6 +78,10 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         if (valid) {
             cb = &B.cblocks[list[h]];
             valid = cb->status_lit == KZG_OK && cb->huf_owner != KZG_INVALID_OWNER;
+            if (valid && !SECOND && cb->lit_regen >= B.huf_long_min) {      // long streams: left to the full-table launch
+                if (st == 0) B.hlist2[atomicAdd(&B.ctr->n_hblocks2, 1u)] = list[h];
+                valid = false;
+            }
         }
         // ---- table: built by the block's four lanes (the rings serve as scratch until the streams start)
         u32 maxbits = KZG_HUF_MAXBITS, nsym = 0, nlong = 0;
@@ -89,7 +93,7 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         __syncwarp();
         if (valid) {
             nlong = kzg_huf_long_entries(sc, maxbits, L1BITS);
-            if (nlong > L2CAP || (!SECOND && cb->lit_regen >= KZG_HUF_LONG_STREAMS)) {      // left to the full-table launch
+            if (nlong > L2CAP) {                // more long codes than the compact layout holds: left to the full-table launch
                 if (!SECOND && st == 0) B.hlist2[atomicAdd(&B.ctr->n_hblocks2, 1u)] = list[h];
                 valid = false;
             }

@@ -273,6 +273,10 @@ int kzg_launch_batch(const KzgBatch& b_in, int sm_count, cudaStream_t stream, cu
     const size_t exec_smem = KZG_EX_SMEM;
     const u32 n = b.n_frames;
     if (n == 0) return 0;
+    // Long literal streams decode faster with full single-level tables (shorter chain per symbol), but only 48 blocks fit
+    // an SM then; with the compact tables 128 do.  Few blocks: the chain counts.  Many: the number of waves does.
+    b.huf_long_min = n > (u32)sm_count * 48u ? 0xFFFFFFFFu : KZG_HUF_LONG_STREAMS;
+    if (const char* e = getenv("KZG_HUF_LONG_MIN")) b.huf_long_min = (u32)strtoul(e, nullptr, 10);
     int k = 0;
 #define KZG_MARK() do { if (ev) cudaEventRecord(ev[k], stream); k++; } while (0)
     const u32 fgrid = (n + 127) / 128;

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 
-from ._lib import InBuffer, KzgError, OutBuffer, lib
+from .._lib import InBuffer, KzgError, OutBuffer, lib
 from .core import ByteArraySlice, SliceTransform
 
 

@@ -9,7 +9,7 @@ import numpy as np
 import corpus
 from oracle.libzstd_ref import load
 from kompressor_b200.batch import BatchEncoder
-from kompressor_b200 import core, zstd
+from kompressor_b200.mirror import core, zstd
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1

@@ -69,7 +69,7 @@ def test_no_cpu_fallback_without_gpu(kzg_lib):
     h = ctypes.c_void_p()
     assert kzg_lib.kzg_ctx_create(ctypes.byref(h), -1) == 64 and not h
     assert not kzg_lib.kzg_createDCtx()
-    from kompressor_b200.zstd import IllegalStateException, ZstdDecompressor
+    from kompressor_b200.mirror.zstd import IllegalStateException, ZstdDecompressor
     with pytest.raises(IllegalStateException):
         ZstdDecompressor()
 

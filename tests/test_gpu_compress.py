@@ -57,7 +57,7 @@ def test_status_codes(enc):
 
 def test_gpu_decoder_reads_gpu_frames(enc, libzstd):
     import corpus
-    from kompressor_b200 import core, zstd
+    from kompressor_b200.mirror import core, zstd
     data = bytes(corpus.generate("logs", 77, 3 << 20)) + bytes(corpus.generate("json", 78, 1 << 20))
     comp = enc.compress(data, checksum=True)
     assert core.transform(zstd.ZstdDecompressor(), comp) == data
@@ -86,7 +86,7 @@ def test_seek_table_stream(enc, libzstd):
     """The frame writer's stream with a seekable index at its end decodes everywhere, and the index gives the frame
     table without a walk."""
     import corpus
-    from kompressor_b200 import core, zstd
+    from kompressor_b200.mirror import core, zstd
     from kompressor_b200.batch import scan_frames
     data = bytes(corpus.generate("json", 91, 1000003))
     comp = enc.compress(data, seek_table=True)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def api(kzg_lib):
-    from kompressor_b200 import core, io, zstd
+    from kompressor_b200.mirror import core, io, zstd
     return core, io, zstd
 
 

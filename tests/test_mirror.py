@@ -5,8 +5,8 @@ import os
 
 import pytest
 
-from kompressor_b200.core import ByteArraySlice, SliceTransform, transform
-from kompressor_b200.io import Buffer, BytesSource, pipe
+from kompressor_b200.mirror.core import ByteArraySlice, SliceTransform, transform
+from kompressor_b200.mirror.io import Buffer, BytesSource, pipe
 
 
 class XorSliceTransform(SliceTransform):
@@ -70,7 +70,7 @@ def test_pipe_small_reads():
 
 def test_pipe_into_sink():
     """SliceTransform.pipe(RawSink) (SliceTransformRawSink.kt:10-47): 8 KiB slices in, finish on close()."""
-    from kompressor_b200.io import BufferSink, transferTo
+    from kompressor_b200.mirror.io import BufferSink, transferTo
     t = XorSliceTransform()
     output = BufferSink()
     sink = pipe(t, output)
