@@ -73,8 +73,8 @@ size_t kzg_write_seek_table(void* dst, size_t cap, const uint64_t* comp_size, co
  *   d_out_size[i]                         out: decoded bytes.  For a frame that failed: the index of the block the error
  *                                         belongs to (the blocks before it are good: the streaming layer hands them over
  *                                         first, as libzstd does); for status 22 the decoded size -- the content is in place,
- *                                         its checksum does not match -- unless bit 63 is set (then: block index, see
- *                                         DESIGN.md "Error behaviour")
+ *                                         its checksum does not match -- unless bit 63 is set (then: block index in the low
+ *                                         30 bits; bit 62 marks the kind of error DESIGN.md "Error behaviour" documents)
  * All pointers are device pointers; the 16-byte aligned chunks around every byte of d_src must be
  * readable (true for any cudaMalloc allocation).  total_src_bytes / total_dst_cap / max_frame_dst_cap
  * are host-side sums / max of the table, used to size the workspace.  Work is enqueued on

@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(128) kzg_finish_kernel(KzgBatch B) {
     // on an error: the index of the block it belongs to (the blocks before it are good; the streaming shim hands them over
     // first, as libzstd does) -- except for a checksum that does not match: the whole content is there
     // (bit 63 marks the one checksum verdict that comes without the content: literals libzstd would have made up)
+    // (bit 62: the error is that kind, whatever the code -- a segment has no checksum of its own, its frame may have one)
     B.out_size[f] = status == KZG_OK || (status == KZG_E_CHECKSUM_WRONG && !fr->lit_garbage) ? len
-                    : ((u64)fr->fail_block | (status == KZG_E_CHECKSUM_WRONG ? 1ull << 63 : 0ull));
+                    : ((u64)fr->fail_block | (status == KZG_E_CHECKSUM_WRONG ? 1ull << 63 : 0ull) | (fr->lit_garbage ? 1ull << 62 : 0ull));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -323,12 +323,15 @@ struct SegFrame {                // the frame that is being decoded in segments
     kzg_seg_state st;
     uint64_t fcs = ~0ull, produced = 0, window = 0;
     bool has_checksum = false;
+    u32 raw_left = 0;            // inside a raw block that arrives in pieces: bytes of it still to come
+    bool raw_last = false;       // ... and whether it is the frame's last block
     std::vector<u8> hist;        // the last `window` bytes of content (in front of them: what is left of the dictionary)
 };
 
 struct kzg_DCtx {
     std::vector<u8> dict;
     uint64_t reported = 0;       // stream bytes the caller has been told are consumed
+    uint64_t goal = 0;           // ... and those libzstd would have taken by now (told as far as the caller's slices reach)
     uint64_t engine = 0;         // stream bytes decoded (or skipped) so far; >= reported
     std::vector<u8> own;         // stream bytes [engine, engine + own.size()) taken over from the caller
     Arena out;                   // decoded bytes not yet handed over: out.p[out_pos, out_size)
@@ -371,7 +374,7 @@ void push_unit(kzg_DCtx* d, size_t out_len, uint64_t in_end, bool frame_end, siz
 
 // Walks whole blocks in [v, v + n): how many, where the last header is, their output bound.  Stops at the last block of
 // the frame, at an incomplete block, at `max_blocks`, or when the bound would exceed `max_out` (never before one block).
-struct BlockRun { size_t bytes = 0, last_hdr = 0, count = 0; uint64_t bound = 0; bool last = false; u32 error = 0; };
+struct BlockRun { size_t bytes = 0, last_hdr = 0, count = 0; uint64_t bound = 0; bool last = false, starved = false; u32 error = 0; };
 BlockRun walk_blocks(const u8* v, size_t n, u32 block_max, uint64_t max_out, size_t max_blocks) {
     BlockRun r;
     size_t q = 0;
@@ -380,7 +383,7 @@ BlockRun walk_blocks(const u8* v, size_t n, u32 block_max, uint64_t max_out, siz
         const u32 type = (bh >> 1) & 3, bsz = bh >> 3;
         if (type == 3 || bsz > block_max) { r.error = KZG_E_CORRUPTION; break; }
         const size_t adv = type == 1 ? 1 : bsz;
-        if (q + 3 + adv > n) break;
+        if (q + 3 + adv > n) { r.starved = true; break; }
         const uint64_t add = type == 2 ? block_max : bsz;
         if (r.count && r.bound + add > max_out) break;
         r.bound += add; r.last_hdr = q; r.count++;
@@ -388,7 +391,16 @@ BlockRun walk_blocks(const u8* v, size_t n, u32 block_max, uint64_t max_out, siz
         r.bytes = q;
         if (bh & 1) { r.last = true; break; }
     }
+    if (!r.last && !r.error && q + 3 > n && r.count < max_blocks) r.starved = true;
     return r;
+}
+
+// A raw block whose content is there only in part (at least one byte of it): libzstd passes raw bytes through as they
+// arrive instead of waiting for the whole block.
+bool partial_raw_at(const u8* p, size_t n, u32 block_max) {
+    if (n < 4) return false;
+    const u32 bh = kzg_rd24(p), type = (bh >> 1) & 3, bsz = bh >> 3;
+    return type == 0 && bsz <= block_max && (size_t)bsz > n - 3;
 }
 
 // One segment of the active frame, decoded behind out_size.  Returns 0 or an error value; *osize / *status as the batch calls.
@@ -439,11 +451,41 @@ size_t seg_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
         else push_unit(d, 0, d->engine, false, err(KZG_E_CHECKSUM_WRONG));
         return ok ? 4 : 0;
     }
+    if (sg.raw_left) {
+        // the next piece of a raw block, wrapped as a raw block of its own so that it takes the same way as everything else
+        // (history, running checksum)
+        if (n == 0) { *incomplete = true; return 0; }
+        const u32 take = n < sg.raw_left ? (u32)n : sg.raw_left;
+        const bool ends_frame = take == sg.raw_left && sg.raw_last;
+        std::vector<u8> piece(3 + (size_t)take);
+        const u32 bh = take << 3;
+        piece[0] = (u8)bh; piece[1] = (u8)(bh >> 8); piece[2] = (u8)(bh >> 16);
+        memcpy(piece.data() + 3, v, take);
+        BlockRun r1; r1.bytes = piece.size(); r1.last_hdr = 0; r1.count = 1; r1.bound = take; r1.last = ends_frame;
+        uint32_t st = 0; uint64_t os = 0;
+        const size_t e = run_segment(d, piece.data(), r1, &st, &os);
+        if (!e && st == 0 && ends_frame && sg.fcs != ~0ull && sg.produced + os != sg.fcs) st = KZG_E_CORRUPTION;
+        if (e || st) { sg.active = false; push_unit(d, 0, d->engine, false, e ? e : err(st)); return 0; }
+        seg_commit(d, os);
+        sg.raw_left -= take;
+        push_unit(d, (size_t)os, d->engine + take, ends_frame && !sg.has_checksum, 0);
+        if (ends_frame) { if (sg.has_checksum) sg.last_seen = true; else sg.active = false; }
+        return take;
+    }
     BlockRun r = walk_blocks(v, n, sg.st.block_max, kSegMax, ~(size_t)0);
     // libzstd compares the content size when it decodes the last block, before handing it over: that block goes alone
     if (r.last && r.count > 1 && sg.fcs != ~0ull) r = walk_blocks(v, n, sg.st.block_max, kSegMax, r.count - 1);
+    // The frame is still arriving: libzstd takes its input block by block, and a pump that offers more input only when
+    // everything has been taken sees that, so the blocks are handed over (and their input reported taken) one at a time.
+    // A frame whose end is in sight goes in runs of up to 32 MiB.
+    else if (r.starved && r.count > 1) r = walk_blocks(v, n, sg.st.block_max, kSegMax, 1);
     if (r.count == 0) {
         if (r.error) { sg.active = false; push_unit(d, 0, d->engine, false, err(r.error)); return 0; }
+        if (partial_raw_at(v, n, sg.st.block_max)) {       // its header is taken now, its bytes piece by piece
+            const u32 bh = kzg_rd24(v);
+            sg.raw_left = bh >> 3; sg.raw_last = (bh & 1) != 0;
+            return 3;
+        }
         *incomplete = true;
         return 0;
     }
@@ -457,8 +499,11 @@ size_t seg_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
     if (st == 0 && r.last && sg.fcs != ~0ull && sg.produced + os != sg.fcs) { st = KZG_E_CORRUPTION; os = 0; }
     if (st != 0) {
         sg.hist = hist0;
-        queue_good_prefix(d, v, n, st0.block_max, (size_t)(os & 0x7FFFFFFFull), st0, d->engine);
+        queue_good_prefix(d, v, n, st0.block_max, (size_t)(os & 0x3FFFFFFFull), st0, d->engine);
         sg.active = false;
+        // literals libzstd would have made up: with a checksum its verdict, at the end of the frame, is
+        // checksum_wrong; the blocks in front of the first such block are handed over, the made-up ones are not
+        if (((os >> 62) & 1) && sg.has_checksum) st = KZG_E_CHECKSUM_WRONG;
         push_unit(d, 0, d->engine, false, err(st));
         return 0;
     }
@@ -478,7 +523,7 @@ size_t seg_start(kzg_DCtx* d, const KzgFrameHeader& h) {
     const u32 block_max = h.window_size < KZG_BLOCK_MAX ? (u32)h.window_size : KZG_BLOCK_MAX;
     const long long content = kzg_segment_begin(&sg.st, block_max, (int)h.has_checksum, d->dict.empty() ? nullptr : d->dict.data(), d->dict.size());
     if (content < 0) { push_unit(d, 0, d->engine, false, err((u32)(-content))); return 0; }
-    sg.active = true; sg.last_seen = false;
+    sg.active = true; sg.last_seen = false; sg.raw_left = 0; sg.raw_last = false;
     sg.fcs = h.fcs; sg.produced = 0; sg.window = h.window_size; sg.has_checksum = h.has_checksum != 0;
     sg.hist.assign(d->dict.end() - (size_t)content, d->dict.end());
     return h.hdr_size;
@@ -522,7 +567,7 @@ size_t engine_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
             // Not complete yet, broken block structure, or too large for one piece: block by block -- but only when a
             // whole block is there to hand over.  A frame whose first block is still arriving just waits: once it is
             // complete it goes through the batch path, where the calls of many handles are merged into one GPU batch.
-            if (nf == 0 && (r.count || r.error)) { start_segments = true; seg_h = h; }
+            if (nf == 0 && (r.count || r.error || partial_raw_at(f + h.hdr_size, rem - h.hdr_size, block_max))) { start_segments = true; seg_h = h; }
             break;
         }
         // (the Frame_Content_Size field is untrusted: a frame cannot regenerate more than its blocks allow)
@@ -571,7 +616,7 @@ size_t engine_round(kzg_DCtx* d, const u8* v, size_t n, bool* incomplete) {
         d->out_size = w;
         const u8* f = v + d->off[i];
         KzgFrameHeader h;
-        const size_t bad_block = (size_t)(d->osize[i] & 0x7FFFFFFFull);
+        const size_t bad_block = (size_t)(d->osize[i] & 0x3FFFFFFFull);
         if ((kzg_rd32(f) & 0xFFFFFFF0u) != KZG_SKIP_MAGIC && kzg_parse_frame_header(f, (size_t)d->size[i], h) == KZG_OK && bad_block > 0 &&
             d->status[i] != KZG_E_DICT_WRONG) {
             d->engine += d->off[i];                          // (seg_start / the prefix units count from the frame's start)
@@ -617,7 +662,7 @@ extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_i
     if (d->sticky_error) return d->sticky_error;
     const u8* src = (const u8*)input->src + input->pos;           // stream offset d->reported
     const size_t avail = input->size - input->pos;
-    const size_t out_entry = output->pos;
+    const size_t out_entry = output->pos, in_entry = input->pos;
     const uint64_t rep_entry = d->reported;                       // stream offset of src[0]
     // bytes of this call the handle has not seen yet: those behind what it decoded ahead or took over earlier
     const uint64_t seen_end = d->engine + d->own.size();
@@ -625,16 +670,29 @@ extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_i
     if (fresh_lo > avail) fresh_lo = avail;                       // (a caller that presents less than before: nothing new)
     bool waiting = false;                                         // the next block / frame is not complete
     size_t result = 0;
+    // input is reported taken up to d->goal, as far as this call's slice reaches (a pump may offer LESS than it offered
+    // before: BufferSliceTransformHelper limits the input slice by the output bytes its reader still wants)
+    auto report = [&]() {
+        const uint64_t lim = rep_entry + avail, to = d->goal < lim ? d->goal : lim;
+        if (to > d->reported) { input->pos += (size_t)(to - d->reported); d->reported = to; }
+    };
+    report();
     for (;;) {
         // ---- hand over
         if (d->unit_head < d->units.size()) {
             Unit& u = d->units[d->unit_head];
             if (u.error) {                                        // libzstd: positions do not advance on an error
                 output->pos = out_entry;
+                input->pos = in_entry;
                 d->sticky_error = u.error;
                 return u.error;
             }
-            if (!d->cur_open) { d->cur_open = true; d->cur_left = u.out_len; }
+            if (!d->cur_open) {
+                // libzstd has taken a block's input when it starts to hand its output over
+                d->cur_open = true; d->cur_left = u.out_len;
+                if (u.in_end > d->goal) d->goal = u.in_end;
+                report();
+            }
             const size_t room = output->size - output->pos;
             const size_t k = d->cur_left < room ? d->cur_left : room;
             if (k) memcpy((u8*)output->dst + output->pos, d->out.p + d->out_pos, k);
@@ -649,7 +707,8 @@ extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_i
                 d->out_pos = d->out_size = 0;
                 if (d->out.cap > (1u << 20)) g_pool.release(d->out);      // large arenas go back to the pool at once
             }
-            if (in_end > d->reported) { input->pos += (size_t)(in_end - d->reported); d->reported = in_end; }
+            if (in_end > d->goal) d->goal = in_end;
+            report();
             if (fe) { result = 0; goto done; }                     // a frame boundary: libzstd returns 0 and stops consuming
             continue;
         }
@@ -676,6 +735,7 @@ extern "C" size_t kzg_decompressStream(kzg_DCtx* d, kzg_outBuffer* output, kzg_i
     }
     if (waiting) {
         const uint64_t all = rep_entry + avail;
+        if (all > d->goal) d->goal = all;
         input->pos = input->size;
         d->reported = all;
         // hint: inside a frame, or idle at a frame start (libzstd: header + block header)

@@ -105,6 +105,12 @@ def decompress_blocks(data: bytes, capacity: int, dictionary: bytes | None = Non
     return dst.raw[:r], 0, blocks
 
 
+def made_up_literals() -> bool:
+    """True if a frame decoded since the last call ended for the one reason documented as a divergence from libzstd
+    (a Huffman stream ran out of bits where libzstd's fast loops make up literals); clears the flag."""
+    return bool(lib().kzo_made_up_literals())
+
+
 def xxh64(data: bytes, seed: int = 0) -> int:
     return lib().kzo_xxh64(data, len(data), seed)
 

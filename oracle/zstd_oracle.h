@@ -92,4 +92,8 @@ const char* kzo_error_name(size_t code);
 #ifdef __cplusplus
 }
 #endif
+/* 1 if a frame decoded since the last call ended because a Huffman stream ran out of bits where libzstd's fast loops
+   make up literals (the documented divergence); clears the flag.  Not thread safe (test tooling). */
+int kzo_made_up_literals(void);
+
 #endif
