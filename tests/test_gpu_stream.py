@@ -392,3 +392,28 @@ def test_largeSample(api, libzstd):                      # ZstdTest.kt:67-82: 25
     compressed = libzstd.compress(data, 3)
     out = core.transform(zstd.ZstdDecompressor(), compressed)
     assert len(out) == n and hashlib.sha256(out).digest() == hashlib.sha256(data).digest()
+
+
+def test_raw_blocks_arrive_in_pieces(both, libzstd):
+    """What the stream fuzzer (tests/stress/gpu_fuzz_stream.py) found: libzstd passes raw blocks through as their bytes
+    arrive, reports a block's input taken when it starts to hand the block over, and a pump that offers more input only
+    when everything is taken sees both.  Incompressible frames (raw blocks), cut short or with a bad checksum, through
+    pumps with several chunk and slice sizes."""
+    rng = np.random.default_rng(373)
+    small = rng.integers(0, 256, 50282, dtype=np.uint8).tobytes()
+    big = rng.integers(0, 256, 700000, dtype=np.uint8).tobytes()
+    f0 = libzstd.compress(small, 3, checksum=True)
+    f1 = bytearray(libzstd.compress(big, 3, checksum=True))
+    good = f0 + bytes(f1) + f0
+    for out_slice, in_chunk in ((100000, 30000), (8192, 8192), (65536, 8192), (64, 65536), (1 << 20, 8192)):
+        out, err, _ = both(good, out_slice, in_chunk=in_chunk)
+        assert err == 0 and out == small + big + small
+    f1[len(f1) // 3] ^= 0x04                             # inside a raw block: only the checksum notices
+    bad = f0 + bytes(f1) + f0
+    for out_slice, in_chunk in ((100000, 30000), (8192, 8192), (1000, None), (1 << 20, 8192), (64, 30000)):
+        out, err, _ = both(bad, out_slice, in_chunk=in_chunk)
+        assert err == 22 and out[:len(small)] == small
+    for cut in (len(f0) + 10, len(f0) + 70000, len(f0) + 131080, len(good) - 2):
+        for out_slice, in_chunk in ((8192, None), (65536, 8192), (100000, 30000)):
+            out, err, _ = both(good[:cut], out_slice, in_chunk=in_chunk)
+            assert err == 0 and (small + big + small).startswith(out)
