@@ -24,15 +24,19 @@
 #include "kzg_stages.cuh"
 
 #define KZG_EX_WARPS 4
+#ifndef KZG_EX_TILE
 #define KZG_EX_TILE 4096u
+#endif
+#ifndef KZG_EX_KEEP
 #define KZG_EX_KEEP 1024u           // flushed history kept in the window after a slide (multiple of 16)
+#endif
 #define KZG_EX_CAP (KZG_EX_TILE - KZG_EX_KEEP - 32u)   // most output one group of lanes may span
 #define KZG_EX_LONG 64u             // literal runs / matches longer than this are copied by the whole warp
 #define KZG_EX_LITSTAGE 1024u       // most literal bytes of one batch that are staged (else read directly)
 #define KZG_EX_LIT_BYTES (KZG_EX_LITSTAGE + 32u)
 #define KZG_EX_MSTAGE 80u           // per-lane match staging: the 16-byte chunks covering <= 64 source bytes
 #define KZG_EX_WARP_SMEM (KZG_EX_TILE + KZG_EX_LIT_BYTES + 32u * KZG_EX_MSTAGE)
-#define KZG_EX_SMEM (KZG_EX_WARPS * KZG_EX_WARP_SMEM + 16u)
+#define KZG_EX_SMEM (KZG_EX_WARPS * KZG_EX_WARP_SMEM + 32u)      // 16 bytes of slack on either side (over-reads of lane_copy_or)
 
 namespace kzg_ex {
 
@@ -124,6 +128,59 @@ __device__ __forceinline__ void lane_copy(u32 d, u32 n, u32 sa, bool fill, u32 f
     }
 }
 
+// Edge-free form of lane_copy for a window whose not yet written bytes are ZERO (kzg_exec_sequences keeps that
+// invariant: the window is cleared at block start, behind every slide and after every warp-wide copy).  The copy
+// walks the aligned destination words: word k takes the source bytes that land on it (two aligned loads, one funnel
+// shift); full words are stored, and the first and the last word -- which may be shared with a neighbouring lane's
+// output -- are OR-ed in with the bytes outside [d, d + n) masked off (RED.OR on shared memory).  No byte stores, no
+// head / tail cases.  Reads up to two aligned words before the first and after the last source byte (callers keep
+// that inside their shared memory; the values are masked off).  A window -> window source must be at least 8 bytes
+// behind its destination: then every load of word k lies below destination word k, which this lane has written.
+__device__ __forceinline__ void red_or32(u32 a, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void lane_copy_or(u32 d, u32 n, u32 sa, bool fill, u32 fillv) {
+    if (n == 0) return;
+    const u32 db = d & 3u, D = d - db;
+    const u32 e = db + n;                                   // end of the copy, in bytes from D
+    u32 rem = (e - 1u) >> 2;                                // destination words after the first
+    const u32 m0 = 0xFFFFFFFFu << (db << 3);
+    const u32 mL = 0xFFFFFFFFu >> (((0u - e) & 3u) << 3);
+    if (fill) {
+        const u32 v = fillv * 0x01010101u;
+        red_or32(D, v & (rem ? m0 : (m0 & mL)));
+        if (rem == 0) return;
+        u32 dd = D + 4;
+        for (--rem; rem; --rem, dd += 4) sts32(dd, v);
+        red_or32(dd, v & mL);
+        return;
+    }
+    const u32 s = sa - db;                                  // the source byte that lands on destination byte D
+    u32 A = s & ~3u;
+    const u32 r = (s & 3u) << 3;
+    u32 lo = lds32(A), hi = lds32(A + 4);
+    red_or32(D, __funnelshift_r(lo, hi, r) & (rem ? m0 : (m0 & mL)));
+    if (rem == 0) return;
+    lo = hi; A += 4;                                        // lo = the word at A
+    u32 dd = D + 4;
+    // full words, up to four per trip (the later ones predicated); loads and stores alternate: a source 8 bytes
+    // behind its destination reads what this trip has written
+    for (--rem; rem;) {
+        const bool p2 = rem > 1, p3 = rem > 2, p4 = rem > 3;
+        const u32 h1 = lds32(A + 4);
+        sts32(dd, __funnelshift_r(lo, h1, r));
+        const u32 h2 = lds32_if(p2, A + 8, 0u);
+        sts32_if(p2, dd + 4, __funnelshift_r(h1, h2, r));
+        const u32 h3 = lds32_if(p3, A + 12, 0u);
+        sts32_if(p3, dd + 8, __funnelshift_r(h2, h3, r));
+        const u32 h4 = lds32_if(p4, A + 16, 0u);
+        sts32_if(p4, dd + 12, __funnelshift_r(h3, h4, r));
+        lo = p4 ? h4 : (p3 ? h3 : (p2 ? h2 : h1));
+        const u32 done = min(rem, 4u);
+        A += done << 2; dd += done << 2; rem -= done;
+    }
+    hi = lds32(A + 4);
+    red_or32(dd, __funnelshift_r(lo, hi, r) & mL);
+}
+
 // Warp-cooperative global -> global copy of disjoint ranges, 16-byte vector stores.
 // HIST: the source is output this warp wrote earlier (read at L2); otherwise read-only input data.
 template <bool HIST>
@@ -196,6 +253,11 @@ __device__ __forceinline__ void flush(Win& w, i32 upto, bool all, u32 lane) {
     }
 }
 
+// Clears window bytes [from, to) (from a multiple of 16): lane_copy_or ORs into unwritten bytes.
+__device__ __forceinline__ void zero_window(u32 tile, u32 from, u32 to, u32 lane) {
+    for (u32 x = from + (lane << 4); x < to; x += 512) sts128(tile + x, make_uint4(0, 0, 0, 0));
+}
+
 // Slides the window down, keeping KZG_EX_KEEP bytes of flushed history below w.F.
 // Requires everything below `cur` (rounded down to 16) to be flushed already.
 __device__ __forceinline__ void slide(Win& w, i32 cur, u32 lane) {
@@ -211,6 +273,8 @@ __device__ __forceinline__ void slide(Win& w, i32 cur, u32 lane) {
         if (x < nbytes) sts128(w.tile + x, v);
         __syncwarp();
     }
+    zero_window(w.tile, nbytes, nbytes + shift, lane);     // what the move vacated: unwritten bytes of the window are zero
+    __syncwarp();
     w.T0 = nT0;
     if (w.Tv < nT0) w.Tv = nT0;
 }
@@ -259,6 +323,8 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
     w.Tv = 0; w.F = 0;
     w.boff = (i64)blk.out_off;
     w.dict_end = B.dict + B.dict_size;
+    zero_window(w.tile, 0u, KZG_EX_TILE, lane);
+    __syncwarp();
     bool err = false, defer = false;
     u64 carry = 0;                       // last record of the previous batch
     u64 rec_next = lane < nseq ? seqs[lane] : 0ull;
@@ -334,7 +400,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
         auto run_group = [&](bool mine, i32 ge) {
             // ---- literal runs of the group (no dependencies)
             if (__builtin_expect(this_staged || lfill, 1)) {
-                lane_copy(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lsrc, lfill, rle);
+                lane_copy_or(w.tile + (u32)((i32)p_out_end - w.T0), mine ? ll : 0u, lsrc, lfill, rle);
             } else if (mine) {       // literal range too large to stage (rare): straight from global memory
                 const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
                 for (u32 k = 0; k < ll; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
@@ -354,8 +420,9 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                 const i32 fin = (i32)__shfl_sync(0xFFFFFFFFu, mdst, __ffs(pm) - 1);   // all below is final
                 const bool go = pending && need <= fin;
                 if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
-                lane_copy(da, (go && !slow) ? ml : 0u, sa, false, 0u);
+                lane_copy_or(da, (go && !slow) ? ml : 0u, sa, false, 0u);
                 if (__builtin_expect(anyslow, 0)) {
+                    __syncwarp();
                     if (go && slow) {     // short period, or a source straddling the flushed / window boundary: bytes in order
                         for (u32 k = 0; k < ml; k++) {
                             const i32 p = spos + (i32)k;
@@ -407,7 +474,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                             if ((u32)(end - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); }
                             const bool in_win = sp0 >= w.Tv, in_glob = sp0 + (i32)l_ml <= w.F;
                             if ((u32)(end - w.T0) <= KZG_EX_TILE && (in_win || in_glob)) {
-                                lane_copy(w.tile + (u32)((i32)l_poe - w.T0), lane == stop ? ll : 0u, lsrc, lfill, rle);
+                                lane_copy_or(w.tile + (u32)((i32)l_poe - w.T0), lane == stop ? ll : 0u, lsrc, lfill, rle);
                                 __syncwarp();
                                 const u32 da = w.tile + (u32)((i32)(l_poe + l_ll) - w.T0);
                                 if (in_win) {
@@ -489,6 +556,8 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                     cur = (i32)(l_poe + l_ll + l_ml);
                     w.F = w.Tv = cur;
                     w.T0 = cur - (i32)((uintptr_t)(out + cur) & 15);
+                    zero_window(w.tile, 0u, KZG_EX_TILE, lane);     // the window starts over, empty
+                    __syncwarp();
                     todo &= ~(1u << stop);
                 }
             }
@@ -530,11 +599,14 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
 // right after over that list only.  Keeping the rare path out of the hot kernel is worth ~5 % of its speed.
 #define KZG_EX_BIG_FRAME_BLOCKS 8u
 template <bool FULL>
-__global__ void __launch_bounds__(KZG_EX_WARPS * 32, 7) kzg_exec_kernel(KzgBatch B) {
+#ifndef KZG_EX_MINBLOCKS
+#define KZG_EX_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(KZG_EX_WARPS * 32, KZG_EX_MINBLOCKS) kzg_exec_kernel(KzgBatch B) {
     using namespace kzg_ex;
     extern __shared__ uint4 smem4[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 smem = (u32)__cvta_generic_to_shared(smem4) + warp * KZG_EX_WARP_SMEM;
+    const u32 smem = (u32)__cvta_generic_to_shared(smem4) + 16u + warp * KZG_EX_WARP_SMEM;
     if (B.ctr->overflow & 3u) return;
     for (;;) {
         u32 f = 0;

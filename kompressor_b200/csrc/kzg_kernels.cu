@@ -304,7 +304,8 @@ int kzg_launch_batch(const KzgBatch& b_in, int sm_count, cudaStream_t stream, cu
     KZG_MARK();
     kzg_bulk_kernel<<<sm_count * 4, KZG_BULK_THREADS, 0, stream>>>(b);
     KZG_MARK();
-    const int exec_per_sm = (int)((227 * 1024) / (exec_smem + 1024));
+    int exec_per_sm = (int)((227 * 1024) / (exec_smem + 1024));
+    if (exec_per_sm > KZG_EX_MINBLOCKS) exec_per_sm = KZG_EX_MINBLOCKS;
     KzgExecChoice ch = kzg_exec_choice();
     if (ch.design == 3 && b.dict_size) ch.design = 1;          // history before the frame: the first design reads it
     // Few frames cannot fill the GPU one warp each: below this many, every frame gets a CTA (kzg_exec4.cuh).
