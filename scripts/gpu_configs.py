@@ -1,5 +1,5 @@
 """Timing of BASELINE.json's other configs on one GPU (development):
-   python scripts/gpu_configs.py [scale] [kind ...]   (scale 1.0 = 1 GiB per config, except level 19; kinds: all)"""
+   python scripts/gpu_configs.py [scale] [kind ...]   (scale 1.0 = 1 GiB per config, except level 19; kinds: all; mixed:64 and mixed:148 = configs[4] with more frames in the batch, only on request)"""
 import sys, time
 sys.path.insert(0, ".")
 import numpy as np
@@ -13,10 +13,11 @@ dec = BatchDecoder()
 dec.set_profiling(True)
 cases = [("logs", 65536, 3, False, False, int(16384 * scale)), ("json", 65536, 3, True, False, int(16384 * scale)),
          ("literal", 65536, 1, False, False, int(16384 * scale)), ("random", 131075, 3, False, False, 256),
-         ("mixed", 4 << 20, 19, False, True, 16)]
+         ("mixed", 4 << 20, 19, False, True, 16), ("mixed:64", 4 << 20, 19, False, True, 64), ("mixed:148", 4 << 20, 19, False, True, 148)]
 for kind, fs, lvl, cs, streamed, n in cases:
-    if only and kind not in only:
+    if (only and kind not in only) or (not only and ":" in kind):      # the larger level-19 batches only on request
         continue
+    kind = kind.split(":")[0]
     t = time.time()
     c = corpus.build(kind, n, fs, lvl, cs, streamed=streamed)
     caps = np.full(n, fs, np.uint64)
