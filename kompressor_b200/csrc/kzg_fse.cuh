@@ -180,7 +180,7 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
 
 }  // namespace kzg_fse
 
-// Queue entry of one sequence of one lane (32 bytes): {hi, lo, pLL, pML} + {ofc}.
+// Queue entry of one sequence of one lane (20 of 32 bytes): {hi, lo, pLL, pML} + {ofc}.
 //   hi:lo  64-bit window at the sequence's bit position        pLL / pML  packed code entries (bits << 24 | base)
 __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B) {
     using namespace kzg_fse;
@@ -202,7 +202,11 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
     const u32 s_pair = s_llx + KZG_FSE_CODE_WORDS * 4 + pair * KZG_FSE_PAIR_SMEM;
     const u32 s_tab = s_pair + (lane << 1);
     const u32 s_ring = s_pair + KZG_FSE_TAB_BYTES + (lane << 7);
-    const u32 s_q = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + (lane << 5);
+    // queue of one sequence (1 KiB): the 16-byte parts of the 32 lanes back to back, then their ofc words -- a warp's
+    // 16-byte access covers 512 contiguous bytes and its 4-byte access 128 (no bank conflicts; entries of 32 bytes per
+    // lane made every one of these accesses 2-way / 8-way conflicted)
+    const u32 s_q = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + (lane << 4);
+    const u32 q_ofc = 512u - lane * 12u;                     // from a lane's 16-byte part to its ofc word
     const u32 s_misc = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES;
     const u32 s_lane = s_misc + 64 + (lane << 2);           // per-lane hand-over word
     const u32 tLL = s_tab, tML = s_tab + (512u << 6), tOF = s_tab + (1024u << 6);
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     const u32 E = ofc + mlb + llb;
                     wide |= act && E > KZG_FSE_WIDE_LIMIT;
                     sts128(qb + u * 1024, hi, lo, pLL, pML);
-                    sts32(qb + u * 1024 + 16, ofc);
+                    sts32(qb + u * 1024 + q_ofc, ofc);
                     // state bits sit right below the E extra bits (valid when E <= 32: E + 26 <= 58 bits)
                     const u32 X = __funnelshift_lc(lo, hi, E);
                     const u32 X2 = X << bLL, X3 = X2 << bML;
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     const bool act = i < nseq;
                     u32 hi, lo, pLL, pML;
                     lds128(qb + u * 1024, hi, lo, pLL, pML);
-                    const u32 ofc = lds32(qb + u * 1024 + 16);
+                    const u32 ofc = lds32(qb + u * 1024 + q_ofc);
                     const u32 llb = pLL >> 24, mlb = pML >> 24;
                     const u32 ofx = __funnelshift_lc(hi, 0u, ofc);
                     const u32 mlx_ = __funnelshift_lc(__funnelshift_l(lo, hi, ofc), 0u, mlb);
