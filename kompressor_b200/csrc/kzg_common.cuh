@@ -178,6 +178,7 @@ struct KzgBatch {
     u32 init_owner[4];
     u32 seg_block_max;
     u32 huf_long_min;   // blocks with at least this many Huffman-coded literals go to the full-table launch (set at launch)
+    u32 lit_ride;       // literal warps in the sequence kernel: 0 = where they can finish (estimate), 1 = always, 2 = never (set at launch)
     // workspace
     KzgFrame* frames;
     KzgBlock* blocks;

@@ -43,8 +43,8 @@
 #define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
 #define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
-// One more warp rides along in every CTA and decodes Huffman literals (kzg_huf_warp_loop) in the shared memory and
-// the issue slots the four sequence warps leave free; it stops taking work when both pairs of its CTA are done.
+// Up to three more warps ride along in every CTA and decode Huffman literals (kzg_huf_warp_loop) in the shared memory
+// and the issue slots the four sequence warps leave free -- where they can finish all of them meanwhile (see the kernel).
 // Literal warps are the odd warps 5, 7, ... (the even ones in between exit at once): they share a scheduler with a post
 // warp, not with a chain warp.  With the two-level Huffman tables a literal warp needs 13 KiB, so up to three fit.
 #define KZG_FSE_LIT_WARPS_MAX 3
@@ -53,6 +53,7 @@
 #define KZG_FSE_SMEM_TOTAL_OF(nlit) (KZG_FSE_SMEM + (nlit) * KZG_HUF_WARP_SMEM)
 #define KZG_FSE_SMEM_TOTAL KZG_FSE_SMEM_TOTAL_OF(KZG_FSE_LIT_WARPS_MAX)
 #define KZG_FSE_DONE_WORD 127                               // in the code-word area: pairs of this CTA that have finished
+#define KZG_FSE_SEQ_CYCLES 200ull                           // one sequence of the chain, in SM clocks (measured: 195 alone, 211 with riders)
 #ifndef KZG_FSE_WIDE_LIMIT
 #define KZG_FSE_WIDE_LIMIT 32u                              // most extra bits per sequence the fast loop extracts (tests lower it)
 #endif
@@ -193,23 +194,27 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
     __syncthreads();
     if (warp >= KZG_FSE_WARPS && !(warp & 1u)) return;
     if (warp > KZG_FSE_WARPS) {                             // a literal warp
-        // only where the sequence work lasts long enough to hide a ticket (8 blocks of literals) behind it
+        // Both stages are serial chains, so the riders are all or nothing: whatever they leave takes kzg_huf_kernel one
+        // full chain however little it is, and riders cost the sequence warps ~7 % (shared-memory traffic).  Measured on
+        // 1 GiB of 64 KiB frames: JSON 0.995 + 0.417 ms with riders that cannot finish, 0.740 + 0.430 without; log text,
+        // whose literals are half as long, finishes under the sequence stage: 0.854 + 0.012 against 0.793 + 0.224.  So
+        // they ride only where they can take (nearly) all the literal tickets before the sequence stage ends, by an estimate
+        // from the batch's counters in units of one sequence of the chain (KZG_FSE_SEQ_CYCLES; a rider's literal symbol
+        // takes ~3/4 of that), and no rider takes a new ticket it could not finish by then (clock64 deadline; every SM
+        // starts its one CTA at the same time).  Riders on SMs whose pairs have no block ride too.
         const u64 nsb = B.ctr->n_sblocks, nhb = B.ctr->n_hblocks, nsq = B.ctr->seq_used;
-        if (nsb == 0 || nhb == 0 || nsq < nsb * 1024u) return;
-        // ... and only where the riding warps can finish ALL the literals meanwhile.  Both stages are serial chains: what
-        // the riders leave takes kzg_huf_kernel one full chain however little it is, and the riders cost the sequence
-        // warps ~7 % (measured on 1 GiB of JSON frames: 0.995 + 0.417 ms with riders, 0.740 + 0.430 without; log text,
-        // whose literals are half as long, finishes under the sequence stage: 0.854 + 0.012 against 0.793 + 0.224).
-        // Estimates in units of one sequence of the chain (~100 ns; a literal symbol of a rider: ~3/4 of that).
-        {
-            const u64 lanes = (u64)gridDim.x * (KZG_FSE_PAIRS * 32u);
-            const u64 est_seq = ((nsb + lanes - 1) / lanes) * (nsq / nsb);
-            const u64 riders = (u64)gridDim.x * ((blockDim.x - KZG_FSE_WARPS * 32u) / 64u);
-            const u64 tickets = (nhb + 7) / 8;
-            const u64 est_lit = ((tickets + riders - 1) / riders) * (B.ctr->lit_used / nhb / 4u) * 3u / 4u;
-            if (est_lit > est_seq) return;
-        }
-        kzg_huf_warp_loop<KZG_HUF_L1_BITS, KZG_HUF_L2CAP, false>(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_SMEM + ((warp - KZG_FSE_WARPS - 1u) >> 1) * KZG_HUF_WARP_SMEM, lane, reinterpret_cast<volatile u32*>(llx + KZG_FSE_DONE_WORD), KZG_FSE_PAIRS);
+        if (nsb == 0 || nhb == 0 || nsq < nsb * 1024u || B.lit_ride == 2u) return;
+        const long long t0 = clock64();
+        const u64 lanes = (u64)gridDim.x * (KZG_FSE_PAIRS * 32u);
+        const u64 est_seq = ((nsb + lanes - 1) / lanes) * (nsq / nsb);
+        const u64 riders = (u64)gridDim.x * ((blockDim.x - KZG_FSE_WARPS * 32u) / 64u);
+        const u64 est_tkt = (B.ctr->lit_used / nhb / 4u) * 3u / 4u;                 // one ticket: the streams of 8 blocks side by side
+        // tickets the riders can finish before the sequence stage ends, against all of them: at least four fifths, or none
+        // (measured: riders that take 87 % leave kzg_huf_kernel a shorter, emptier launch and win 2-5 %; 45 % loses 2 %)
+        const u64 fit = est_tkt ? est_seq / est_tkt : 0xFFFFull;
+        if (B.lit_ride == 0u && fit * riders * 5u < ((nhb + 7) / 8) * 4u) return;
+        const long long deadline = t0 + (long long)((est_seq > est_tkt ? est_seq - est_tkt : 0ull) * KZG_FSE_SEQ_CYCLES) + 1;
+        kzg_huf_warp_loop<KZG_HUF_L1_BITS, KZG_HUF_L2CAP, false>(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_SMEM + ((warp - KZG_FSE_WARPS - 1u) >> 1) * KZG_HUF_WARP_SMEM, lane, deadline, 0xFFFFFFFFu);
         return;
     }
     const u32 s_llx = smem_addr(llx), s_mlx = s_llx + 36 * 4;

@@ -48,13 +48,14 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 
 }  // namespace kzg_huf
 
-// The work loop of one warp (wbase: its KZG_HUF_WARP_SMEM bytes of shared memory).  With `stop` set, the warp takes no
-// new ticket once *stop reaches stop_at: that is how the warp that rides along in the sequence kernel (kzg_fse.cuh)
-// leaves when the sequence work of its SM is done; kzg_huf_kernel then finishes what is left.
+// The work loop of one warp (wbase: its KZG_HUF_WARP_SMEM bytes of shared memory).  With `deadline` set (a clock64()
+// value), the warp takes no new ticket after it: that is how the warps that ride along in the sequence kernel
+// (kzg_fse.cuh) leave when the sequence work is about to end; kzg_huf_kernel then finishes what is left.  `long_min`:
+// blocks with at least this many literals are left to the full-table launch (riders take them all).
 // L1BITS / L2CAP: first-level index width and second-level entries per block in this warp's layout; SECOND: the launch
 // that takes the blocks the compact launch left (work list hlist2), with L1BITS = KZG_HUF_MAXBITS (full tables).
 template <u32 L1BITS, u32 L2CAP, bool SECOND>
-__device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, u32 lane, const volatile u32* stop, u32 stop_at) {
+__device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, u32 lane, long long deadline, u32 long_min) {
     using namespace kzg_huf;
     const u32 hb = lane >> 2, st = lane & 3;
     constexpr u32 L1_BYTES = 2u << L1BITS;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
     const u32* list = SECOND ? B.hlist2 : B.hlist;
     for (;;) {
         u32 g = 0xFFFFFFFFu;
-        if (lane == 0 && !(stop && *stop >= stop_at)) g = atomicAdd(SECOND ? &B.ctr->ticket_huf2 : &B.ctr->ticket_huf, 1u);
+        if (lane == 0 && !(deadline && clock64() > deadline)) g = atomicAdd(SECOND ? &B.ctr->ticket_huf2 : &B.ctr->ticket_huf, 1u);
         g = __shfl_sync(0xFFFFFFFFu, g, 0);
         if (g == 0xFFFFFFFFu || (u64)g * 8 >= n) break;
         const u32 h = g * 8 + hb;
@@ -78,7 +79,7 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         if (valid) {
             cb = &B.cblocks[list[h]];
             valid = cb->status_lit == KZG_OK && cb->huf_owner != KZG_INVALID_OWNER;
-            if (valid && !SECOND && cb->lit_regen >= B.huf_long_min) {      // long streams: left to the full-table launch
+            if (valid && !SECOND && cb->lit_regen >= long_min) {      // long streams: left to the full-table launch
                 if (st == 0) B.hlist2[atomicAdd(&B.ctr->n_hblocks2, 1u)] = list[h];
                 valid = false;
             }
@@ -239,5 +240,5 @@ template <u32 L1BITS, u32 L2CAP, bool SECOND>
 __global__ void __launch_bounds__(KZG_HUF_WARPS * 32) kzg_huf_kernel(KzgBatch B) {
     extern __shared__ uint4 smem4[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    kzg_huf_warp_loop<L1BITS, L2CAP, SECOND>(B, reinterpret_cast<u8*>(smem4) + warp * KZG_HUF_WARP_SMEM_OF(L1BITS, L2CAP), lane, nullptr, 0);
+    kzg_huf_warp_loop<L1BITS, L2CAP, SECOND>(B, reinterpret_cast<u8*>(smem4) + warp * KZG_HUF_WARP_SMEM_OF(L1BITS, L2CAP), lane, 0ll, B.huf_long_min);
 }

@@ -278,6 +278,8 @@ int kzg_launch_batch(const KzgBatch& b_in, int sm_count, cudaStream_t stream, cu
     // an SM then; with the compact tables 128 do.  Few blocks: the chain counts.  Many: the number of waves does.
     b.huf_long_min = n > (u32)sm_count * 48u ? 0xFFFFFFFFu : KZG_HUF_LONG_STREAMS;
     if (const char* e = getenv("KZG_HUF_LONG_MIN")) b.huf_long_min = (u32)strtoul(e, nullptr, 10);
+    b.lit_ride = 0;
+    if (const char* e = getenv("KZG_FSE_RIDE")) b.lit_ride = (u32)strtoul(e, nullptr, 10);     // development knob
     int k = 0;
 #define KZG_MARK() do { if (ev) cudaEventRecord(ev[k], stream); k++; } while (0)
     const u32 fgrid = (n + 127) / 128;
