@@ -41,7 +41,8 @@
 #define KZG_FSE_Q_BYTES (2 * KZG_FSE_SERVICE * 1024)        // per pair: 2 buffers x 4 sequences x 32 lanes x 32 B
 #define KZG_FSE_MISC_BYTES 512                              // per pair: ticket, trip count, per-lane hand-over words
 #define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
-#define KZG_FSE_CODE_WORDS 128                              // 36 LL + 53 ML packed code entries, padded
+#define KZG_FSE_CODE_WORDS 192                              // 36 LL + 53 ML packed code entries, padded to 128 words; then (from byte 512,
+                                                            // aligned to 64) the extra-bit counts alone, one BYTE per code: 64 B LL, 64 B ML
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
 // Up to three more warps ride along in every CTA and decode Huffman literals (kzg_huf_warp_loop) in the shared memory
 // and the issue slots the four sequence warps leave free -- where they can finish all of them meanwhile (see the kernel).
@@ -64,6 +65,7 @@ __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_gen
 __device__ __forceinline__ u32 lds16(u32 a) { u16 v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((u16)v)); }
 __device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ u32 lds8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(u32 a, u32 x, u32 y, u32 z, u32 w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -181,8 +183,8 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
 
 }  // namespace kzg_fse
 
-// Queue entry of one sequence of one lane (20 of 32 bytes): {hi, lo, pLL, pML} + {ofc}.
-//   hi:lo  64-bit window at the sequence's bit position        pLL / pML  packed code entries (bits << 24 | base)
+// Queue entry of one sequence of one lane (16 bytes): {hi, lo, eLL | eML << 16, ofc}.
+//   hi:lo  64-bit window at the sequence's bit position        eLL / eML  the LL / ML table cells (code in bits 0-5)
 __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B) {
     using namespace kzg_fse;
     extern __shared__ uint4 smem4[];
@@ -190,7 +192,14 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 pair = warp >> 1;
     const bool chain = (warp & 1u) == 0;                   // even warp: chain, odd warp: post
-    for (u32 k = threadIdx.x; k < KZG_FSE_CODE_WORDS; k += blockDim.x) llx[k] = k < 89 ? B.code_tables[k] : 0u;
+    for (u32 k = threadIdx.x; k < 128u; k += blockDim.x) llx[k] = k < 89 ? B.code_tables[k] : 0u;
+    // the extra-bit counts of the LL / ML codes as bytes, each table 64-byte aligned: its address is one LOP3 of the cell
+    const u32 s_llb = (smem_addr(llx) + 512u + 63u) & ~63u, s_mlb = s_llb + 64u;
+    if (threadIdx.x < 64u) {
+        const u32 k = threadIdx.x;
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(s_llb + k), "r"(k < 36u ? B.code_tables[k] >> 24 : 0u) : "memory");
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(s_mlb + k), "r"(k < 53u ? B.code_tables[36u + k] >> 24 : 0u) : "memory");
+    }
     __syncthreads();
     if (warp >= KZG_FSE_WARPS && !(warp & 1u)) return;
     if (warp > KZG_FSE_WARPS) {                             // a literal warp
@@ -221,11 +230,9 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
     const u32 s_pair = s_llx + KZG_FSE_CODE_WORDS * 4 + pair * KZG_FSE_PAIR_SMEM;
     const u32 s_tab = s_pair + (lane << 1);
     const u32 s_ring = s_pair + KZG_FSE_TAB_BYTES + (lane << 7);
-    // queue of one sequence (1 KiB): the 16-byte parts of the 32 lanes back to back, then their ofc words -- a warp's
-    // 16-byte access covers 512 contiguous bytes and its 4-byte access 128 (no bank conflicts; entries of 32 bytes per
-    // lane made every one of these accesses 2-way / 8-way conflicted)
+    // queue slot of one sequence: 16 bytes per lane, the lanes back to back (a warp's access covers 512 contiguous bytes:
+    // no bank conflicts; entries of 32 bytes per lane made every access 2-way / 8-way conflicted)
     const u32 s_q = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + (lane << 4);
-    const u32 q_ofc = 512u - lane * 12u;                     // from a lane's 16-byte part to its ofc word
     const u32 s_misc = s_pair + KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES;
     const u32 s_lane = s_misc + 64 + (lane << 2);           // per-lane hand-over word
     const u32 tLL = s_tab, tML = s_tab + (512u << 6), tOF = s_tab + (1024u << 6);
@@ -344,6 +351,14 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             const u32 szLL = 1u << j.logLL, szOF = 1u << j.logOF, szML = 1u << j.logML;
             const u32 kLL = j.logLL - 31u, kOF = j.logOF - 31u, kML = j.logML - 31u;   // nbBits = k + clz(next)
             bool wide = false;                   // a sequence with more than 32 extra bits was seen
+            // The loop is one dependency chain per sequence (cell -> extra-bit counts -> E -> state bits -> next cell),
+            // and every dependent instruction on it costs a lone warp ~12 clocks, a shared-memory load ~32.  So the chain
+            // carries the ADDRESS of each state's cell, not the state (the part of the next address that does not depend on
+            // the bits read -- table base + ((next << nb) - size) * 64 -- is computed beside the chain), the extra-bit
+            // counts come from byte tables whose address is a single LOP3 of the cell, and E is a single three-input add:
+            // two loads and five instructions between one LL cell and the next (it was two loads and nine).
+            u32 aLL = tLL + (sLL << 6), aML = tML + (sML << 6), aOF = tOF + (sOF << 6);
+            const u32 zLL = tLL - (szLL << 6), zML = tML - (szML << 6), zOF = tOF - (szOF << 6);
             for (u32 t = 0; t < nint; t++) {
                 const u32 buf = t & 1u;
                 if (t >= 2) bar_sync(BAR_EMPTY + buf);            // the post warp is done with this buffer
@@ -368,30 +383,28 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }     // rare: wait for everything
                 }
                 const u32 i0 = t * KZG_FSE_SERVICE;
-                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 1024);
+                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 512);
 #pragma unroll
                 for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
                     const u32 i = i0 + u;
                     const bool act = i < nseq, notlast = i + 1 < nseq;
-                    const u32 eLL = lds16(tLL + (sLL << 6)), eML = lds16(tML + (sML << 6)), eOF = lds16(tOF + (sOF << 6));
+                    const u32 eLL = lds16(aLL), eML = lds16(aML), eOF = lds16(aOF);
                     u32 hi, lo;
                     KZG_FSE_WINDOW(hi, lo);
                     const u32 ofc = eOF & 63u;
-                    const u32 pLL = lds32(s_llx + ((eLL & 63u) << 2)), pML = lds32(s_mlx + ((eML & 63u) << 2));
-                    const u32 llb = pLL >> 24, mlb = pML >> 24;
+                    const u32 llb = lds8(s_llb | (eLL & 63u)), mlb = lds8(s_mlb | (eML & 63u));
                     const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
                     // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
                     const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
                     const u32 E = ofc + mlb + llb;
                     wide |= act && E > KZG_FSE_WIDE_LIMIT;
-                    sts128(qb + u * 1024, hi, lo, pLL, pML);
-                    sts32(qb + u * 1024 + q_ofc, ofc);
+                    sts128(qb + u * 512, hi, lo, eLL | (eML << 16), ofc);
                     // state bits sit right below the E extra bits (valid when E <= 32: E + 26 <= 58 bits)
                     const u32 X = __funnelshift_lc(lo, hi, E);
                     const u32 X2 = X << bLL, X3 = X2 << bML;
-                    sLL = (nLL << bLL) - szLL + __funnelshift_lc(X, 0u, bLL);
-                    sML = (nML << bML) - szML + __funnelshift_lc(X2, 0u, bML);
-                    sOF = (nOF << bOF) - szOF + __funnelshift_lc(X3, 0u, bOF);
+                    aLL = zLL + (nLL << (bLL + 6u)) + (__funnelshift_lc(X, 0u, bLL) << 6);
+                    aML = zML + (nML << (bML + 6u)) + (__funnelshift_lc(X2, 0u, bML) << 6);
+                    aOF = zOF + (nOF << (bOF + 6u)) + (__funnelshift_lc(X3, 0u, bOF) << 6);
                     P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
                 }
                 __threadfence_block();
@@ -419,14 +432,14 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                 const u32 buf = t & 1u;
                 bar_sync(BAR_FULL + buf);
                 const u32 i0 = t * KZG_FSE_SERVICE;
-                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 1024);
+                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 512);
 #pragma unroll
                 for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
                     const u32 i = i0 + u;
                     const bool act = i < nseq;
-                    u32 hi, lo, pLL, pML;
-                    lds128(qb + u * 1024, hi, lo, pLL, pML);
-                    const u32 ofc = lds32(qb + u * 1024 + q_ofc);
+                    u32 hi, lo, cells, ofc;
+                    lds128(qb + u * 512, hi, lo, cells, ofc);
+                    const u32 pLL = lds32(s_llx + ((cells & 63u) << 2)), pML = lds32(s_mlx + ((cells >> 14) & 252u));
                     const u32 llb = pLL >> 24, mlb = pML >> 24;
                     const u32 ofx = __funnelshift_lc(hi, 0u, ofc);
                     const u32 mlx_ = __funnelshift_lc(__funnelshift_l(lo, hi, ofc), 0u, mlb);
