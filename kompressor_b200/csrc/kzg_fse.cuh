@@ -37,8 +37,11 @@
 #define KZG_FSE_TAB_BYTES (KZG_FSE_CELLS * 64)              // per pair: 32 lanes x 1280 cells x 2 B
 #define KZG_FSE_RING_CHUNKS 8
 #define KZG_FSE_RING_BYTES (KZG_FSE_RING_CHUNKS * 512)      // per pair: 32 lanes x (8 chunks x 16 B, contiguous per lane)
-#define KZG_FSE_SERVICE 4                                   // sequences per hand-over / between ring service points
-#define KZG_FSE_Q_BYTES (2 * KZG_FSE_SERVICE * 1024)        // per pair: 2 buffers x 4 sequences x 32 lanes x 32 B
+#define KZG_FSE_SERVICE 4                                   // sequences between ring service points
+#ifndef KZG_FSE_HAND
+#define KZG_FSE_HAND 8                                      // sequences per hand-over (a multiple of KZG_FSE_SERVICE)
+#endif
+#define KZG_FSE_Q_BYTES (2 * KZG_FSE_HAND * 512)            // per pair: 2 buffers x 8 sequences x 32 lanes x 16 B
 #define KZG_FSE_MISC_BYTES 512                              // per pair: ticket, trip count, per-lane hand-over words
 #define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
 #define KZG_FSE_CODE_WORDS 192                              // 36 LL + 53 ML packed code entries, padded to 128 words; then (from byte 512,
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
         bar_sync(BAR_PAIR);
         const u32 nmax = lds32(s_misc + 4);
         nseq = lds32(s_lane);
-        const u32 nint = (nmax + KZG_FSE_SERVICE - 1) / KZG_FSE_SERVICE;     // hand-overs in this round
+        const u32 nint = (nmax + KZG_FSE_HAND - 1) / KZG_FSE_HAND;     // hand-overs in this round
 
         if (chain) {
             // =================================================================== chain warp
@@ -362,6 +365,8 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             for (u32 t = 0; t < nint; t++) {
                 const u32 buf = t & 1u;
                 if (t >= 2) bar_sync(BAR_EMPTY + buf);            // the post warp is done with this buffer
+#pragma unroll
+                for (u32 h = 0; h < KZG_FSE_HAND / KZG_FSE_SERVICE; h++) {
                 {
                     // ring service (warp-uniform point). Chunks issued two service points ago are complete now;
                     // up to 3 new chunks (384 bits >= 4 x 89, the most four sequences can consume) are requested,
@@ -382,8 +387,8 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     const i32 need_lo = max((P - 451) >> 7, 0);
                     if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }     // rare: wait for everything
                 }
-                const u32 i0 = t * KZG_FSE_SERVICE;
-                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 512);
+                const u32 i0 = t * KZG_FSE_HAND + h * KZG_FSE_SERVICE;
+                const u32 qb = s_q + buf * (KZG_FSE_HAND * 512) + h * (KZG_FSE_SERVICE * 512);
 #pragma unroll
                 for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
                     const u32 i = i0 + u;
@@ -406,6 +411,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     aML = zML + (nML << (bML + 6u)) + (__funnelshift_lc(X2, 0u, bML) << 6);
                     aOF = zOF + (nOF << (bOF + 6u)) + (__funnelshift_lc(X3, 0u, bOF) << 6);
                     P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
+                }
                 }
                 __threadfence_block();
                 bar_arrive(BAR_FULL + buf);
@@ -431,10 +437,10 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             for (u32 t = 0; t < nint; t++) {
                 const u32 buf = t & 1u;
                 bar_sync(BAR_FULL + buf);
-                const u32 i0 = t * KZG_FSE_SERVICE;
-                const u32 qb = s_q + buf * (KZG_FSE_SERVICE * 512);
+                const u32 i0 = t * KZG_FSE_HAND;
+                const u32 qb = s_q + buf * (KZG_FSE_HAND * 512);
 #pragma unroll
-                for (u32 u = 0; u < KZG_FSE_SERVICE; u++) {
+                for (u32 u = 0; u < KZG_FSE_HAND; u++) {
                     const u32 i = i0 + u;
                     const bool act = i < nseq;
                     u32 hi, lo, cells, ofc;
