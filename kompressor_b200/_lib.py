@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_int, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkzg.so")
+LIB_PATH = os.environ.get("KZG_LIB_PATH") or os.path.join(_HERE, "libkzg.so")      # (override: kernel variant sweeps, scripts/variant_sweep.sh)
 
 
 class KzgError(RuntimeError):

@@ -41,6 +41,9 @@
 #ifndef KZG_FSE_HAND
 #define KZG_FSE_HAND 8                                      // sequences per hand-over (a multiple of KZG_FSE_SERVICE)
 #endif
+#ifndef KZG_FSE_INFLIGHT
+#define KZG_FSE_INFLIGHT 3                                  // copy groups (one per ring service) that may still be in flight at a service point: 1..3
+#endif
 #define KZG_FSE_Q_BYTES (2 * KZG_FSE_HAND * 512)            // per pair: 2 buffers x 8 sequences x 32 lanes x 16 B
 #define KZG_FSE_MISC_BYTES 512                              // per pair: ticket, trip count, per-lane hand-over words
 #define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
 
         // ---- bitstream set-up (chain warp); the effective sequence count goes to the post warp
         const u8* base = nullptr;
-        i32 next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0, P = 0;
+        i32 next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0, pend3 = 0, pend4 = 0, P = 0;
         u32 sLL = 0, sOF = 0, sML = 0;
         u32 nseq = j.nseq;
         bar_sync(BAR_PAIR);                                  // tables complete (all three, both warps)
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             }
             cp_commit();
             cp_wait<0>();
-            ready_lo = pend1 = pend2 = next_c + 1;
+            ready_lo = pend1 = pend2 = pend3 = pend4 = next_c + 1;
             // Lanes without a block keep executing the loop on a frozen position: give each its own ring word, or all of
             // them read the same bank of their (128-byte strided) rings three times per sequence -- a 32-way conflict
             // that doubles the time of a group with few blocks (small batches).
@@ -364,16 +367,24 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             const u32 zLL = tLL - (szLL << 6), zML = tML - (szML << 6), zOF = tOF - (szOF << 6);
             for (u32 t = 0; t < nint; t++) {
                 const u32 buf = t & 1u;
+#ifndef DBG_NOQ
                 if (t >= 2) bar_sync(BAR_EMPTY + buf);            // the post warp is done with this buffer
+#endif
 #pragma unroll
                 for (u32 h = 0; h < KZG_FSE_HAND / KZG_FSE_SERVICE; h++) {
                 {
                     // ring service (warp-uniform point). Chunks issued two service points ago are complete now;
                     // up to 3 new chunks (384 bits >= 4 x 89, the most four sequences can consume) are requested,
                     // as far down as the ring allows (the slot of chunk c + 8 must be dead).
-                    cp_wait<1>();
-                    ready_lo = pend2;
+#ifdef DBG_NORING
+                    if (t > 0x7fffffffu)
+#endif
+                    cp_wait<KZG_FSE_INFLIGHT>();
+                    ready_lo = KZG_FSE_INFLIGHT == 1 ? pend2 : (KZG_FSE_INFLIGHT == 2 ? pend3 : pend4);
                     const i32 cP = P >> 7;
+#ifdef DBG_NORING
+                    if (t > 0x7fffffffu) {
+#endif
                     const i32 want = min(min(next_c - (cP - KZG_FSE_RING_CHUNKS), next_c + 1), 3);
                     const u8* gsrc = base + ((i64)next_c << 4);
                     cp_async16_if(want > 0, s_ring + (((u32)next_c & 7u) << 4), gsrc);
@@ -381,11 +392,16 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     cp_async16_if(want > 2, s_ring + (((u32)(next_c - 2) & 7u) << 4), gsrc - 32);
                     next_c -= max(want, 0);
                     cp_commit();
+                    pend4 = pend3;
+                    pend3 = pend2;
                     pend2 = pend1;
                     pend1 = next_c + 1;
                     // lowest chunk the next four sequences can touch: 4 x 89 bits + 64-bit window + 31
                     const i32 need_lo = max((P - 451) >> 7, 0);
-                    if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }     // rare: wait for everything
+                    if (need_lo < ready_lo) { cp_wait<0>(); ready_lo = pend4 = pend3 = pend2 = pend1; }     // rare: wait for everything
+#ifdef DBG_NORING
+                    }
+#endif
                 }
                 const u32 i0 = t * KZG_FSE_HAND + h * KZG_FSE_SERVICE;
                 const u32 qb = s_q + buf * (KZG_FSE_HAND * 512) + h * (KZG_FSE_SERVICE * 512);
@@ -395,15 +411,25 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     const bool act = i < nseq, notlast = i + 1 < nseq;
                     const u32 eLL = lds16(aLL), eML = lds16(aML), eOF = lds16(aOF);
                     u32 hi, lo;
+#ifdef DBG_NOWIN
+                    hi = eLL * 2654435761u; lo = eML * 40503u;
+#else
                     KZG_FSE_WINDOW(hi, lo);
+#endif
                     const u32 ofc = eOF & 63u;
+#ifdef DBG_NOCODE
+                    const u32 llb = 0, mlb = 0;
+#else
                     const u32 llb = lds8(s_llb | (eLL & 63u)), mlb = lds8(s_mlb | (eML & 63u));
+#endif
                     const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
                     // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
                     const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
                     const u32 E = ofc + mlb + llb;
                     wide |= act && E > KZG_FSE_WIDE_LIMIT;
+#ifndef DBG_NOQ
                     sts128(qb + u * 512, hi, lo, eLL | (eML << 16), ofc);
+#endif
                     // state bits sit right below the E extra bits (valid when E <= 32: E + 26 <= 58 bits)
                     const u32 X = __funnelshift_lc(lo, hi, E);
                     const u32 X2 = X << bLL, X3 = X2 << bML;
@@ -413,8 +439,10 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
                 }
                 }
+#ifndef DBG_NOQ
                 __threadfence_block();
                 bar_arrive(BAR_FULL + buf);
+#endif
             }
             cp_wait<0>();
             // hand the verdict on the bitstream to the post warp: bit 0 = consumed exactly, bit 1 = general path needed
@@ -436,7 +464,9 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
             u64* out = j.out;
             for (u32 t = 0; t < nint; t++) {
                 const u32 buf = t & 1u;
+#ifndef DBG_NOQ
                 bar_sync(BAR_FULL + buf);
+#endif
                 const u32 i0 = t * KZG_FSE_HAND;
                 const u32 qb = s_q + buf * (KZG_FSE_HAND * 512);
 #pragma unroll
@@ -472,8 +502,10 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     if (act) out[i] = kzg_pack_seq(off, lit_end & 0x3FFFFu, out_end & 0x3FFFFu);
                 }
                 if (t + 2 < nint) {          // matched by the chain warp's wait two hand-overs later
+#ifndef DBG_NOQ
                     __threadfence_block();   // the queue reads above are performed before the buffer is handed back
                     bar_arrive(BAR_EMPTY + buf);
+#endif
                 }
             }
             bar_sync(BAR_PAIR);

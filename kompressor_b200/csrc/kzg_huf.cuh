@@ -22,6 +22,9 @@
 #include "kzg_stages.cuh"
 
 #define KZG_HUF_WARPS 2
+#ifndef KZG_HUF_INFLIGHT
+#define KZG_HUF_INFLIGHT 3                                   // copy groups (one per ring service) that may still be in flight at a service point: 1..3
+#endif
 #define KZG_HUF_L2CAP 64u                                    // second-level entries per block, compact layout
 #define KZG_HUF_LONG_STREAMS 32768u                          // blocks with at least this many literals go to the full-table launch
 #define KZG_HUF_RING_BYTES (32u * 128u)                      // per warp: 32 lanes x 8 chunks x 16 B
@@ -109,7 +112,7 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         u8* dst = nullptr;
         u32 cnt = 0;
         // (lanes without a stream run the loops on a frozen position: one ring word each, or they all hit the same bank)
-        i32 P = (i32)(lane << 5), lowbits = 0, next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0;
+        i32 P = (i32)(lane << 5), lowbits = 0, next_c = -1, ready_lo = 0, pend1 = 0, pend2 = 0, pend3 = 0, pend4 = 0;
         bool mine = valid && st < cb->n_streams, bad = false;
         if (mine) {
             const u32 regen = cb->lit_regen;
@@ -137,7 +140,7 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         }
         cp_commit();
         cp_wait<0>();
-        ready_lo = pend1 = pend2 = next_c + 1;
+        ready_lo = pend1 = pend2 = pend3 = pend4 = next_c + 1;
         const u32 sh = 32u - maxbits, sshift = kzg_huf_split(maxbits, L1BITS);
 
 #define KZG_HUF_WINDOW(hi, lo)                                                     \
@@ -151,8 +154,8 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
         }
 #define KZG_HUF_SERVICE(need_bits)                                                                        \
         {                                                                                                 \
-            cp_wait<1>();                                                                                 \
-            ready_lo = pend2;                                                                             \
+            cp_wait<KZG_HUF_INFLIGHT>();                                                                  \
+            ready_lo = KZG_HUF_INFLIGHT == 1 ? pend2 : (KZG_HUF_INFLIGHT == 2 ? pend3 : pend4);           \
             const i32 cP_ = P >> 7;                                                                       \
             const i32 want_ = min(min(next_c - (cP_ - 8), next_c + 1), 2);                                \
             const u8* g_ = base + ((i64)next_c << 4);                                                     \
@@ -160,10 +163,12 @@ __device__ __forceinline__ void kzg_huf_warp_loop(const KzgBatch& B, u8* wbase, 
             cp_async16_if(want_ > 1, s_ring + (((u32)(next_c - 1) & 7u) << 4), g_ - 16);                  \
             next_c -= max(want_, 0);                                                                      \
             cp_commit();                                                                                  \
+            pend4 = pend3;                                                                                \
+            pend3 = pend2;                                                                                \
             pend2 = pend1;                                                                                \
             pend1 = next_c + 1;                                                                           \
             const i32 need_lo_ = max((P - (i32)(need_bits)) >> 7, 0);                                     \
-            if (need_lo_ < ready_lo) { cp_wait<0>(); ready_lo = pend2 = pend1; }                          \
+            if (need_lo_ < ready_lo) { cp_wait<0>(); ready_lo = pend4 = pend3 = pend2 = pend1; }          \
         }
         // one symbol from the top of hi:lo; advances the window and `used`
 #define KZG_HUF_SYM(sym, hi, lo, used)                                             \
