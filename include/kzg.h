@@ -148,6 +148,10 @@ uint32_t kzg_segment_checksum(const kzg_seg_state* st);
  * how many stages it wrote (0 if profiling was off). */
 int kzg_ctx_set_profiling(kzg_ctx* ctx, int enable);
 int kzg_last_stage_ms(kzg_ctx* ctx, float* ms, const char** names, int max_stages);
+/* The same for the batch enqueued `age` batches before the newest (0 = the newest; the last 32 profiled batches are
+ * kept), so that batches enqueued back to back need no host synchronisation in between to be timed.  The caller
+ * synchronises the stream first.  Returns 0 if that batch is not (or no longer) kept. */
+int kzg_stage_ms_history(kzg_ctx* ctx, int age, float* ms, const char** names, int max_stages);
 
 /* ------------------------------------------------------------------ Layer A, compress side: batch frame writer
  * SURVEY.md section 8(f) rank 4, the step before the path.  Replaces, for producers that hold many chunks,

@@ -35,7 +35,7 @@ class OutBuffer(Structure):
 EXPORTS = [
     "kzg_isError", "kzg_getErrorName", "kzg_versionString", "kzg_ctx_create", "kzg_ctx_destroy", "kzg_scan_frames",
     "kzg_decompress_batch_device", "kzg_batch_finish", "kzg_decompress_batch_host", "kzg_host_alloc", "kzg_host_free",
-    "kzg_last_batch_stats", "kzg_ctx_set_dictionary", "kzg_ctx_set_profiling", "kzg_last_stage_ms", "kzg_createDCtx", "kzg_freeDCtx", "kzg_DCtx_loadDictionary", "kzg_decompressStream",
+    "kzg_last_batch_stats", "kzg_ctx_set_dictionary", "kzg_ctx_set_profiling", "kzg_last_stage_ms", "kzg_stage_ms_history", "kzg_createDCtx", "kzg_freeDCtx", "kzg_DCtx_loadDictionary", "kzg_decompressStream",
     "kzg_enc_create", "kzg_enc_destroy", "kzg_compress_bound", "kzg_compress_batch_device", "kzg_enc_finish",
     "kzg_compress_batch_host", "kzg_enc_set_profiling", "kzg_enc_last_stage_ms",
     "kzg_createCCtx", "kzg_freeCCtx", "kzg_CCtx_setParameter", "kzg_CCtx_loadDictionary", "kzg_compressStream2",
@@ -85,6 +85,8 @@ def lib() -> ctypes.CDLL:
     L.kzg_ctx_set_profiling.restype = c_int
     L.kzg_last_stage_ms.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
     L.kzg_last_stage_ms.restype = c_int
+    L.kzg_stage_ms_history.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int]
+    L.kzg_stage_ms_history.restype = c_int
     L.kzg_enc_create.argtypes = [POINTER(c_void_p), c_int]
     L.kzg_enc_create.restype = c_int
     L.kzg_enc_destroy.argtypes = [c_void_p]

@@ -150,11 +150,12 @@ class BatchDecoder:
     def set_profiling(self, enable: bool = True) -> None:
         self._L.kzg_ctx_set_profiling(self._h, int(enable))
 
-    def stage_ms(self) -> dict:
-        """Per-stage device time (ms) of the last finished batch; {} if profiling is off."""
+    def stage_ms(self, age: int = 0) -> dict:
+        """Per-stage device time (ms) of the last finished batch (age 0) or of the batch enqueued `age` batches before
+        it (the library keeps the events of the last 32 profiled batches); {} if profiling is off or nothing is kept."""
         ms = (ctypes.c_float * 16)()
         names = (ctypes.c_char_p * 16)()
-        n = self._L.kzg_last_stage_ms(self._h, ms, names, 16)
+        n = self._L.kzg_stage_ms_history(self._h, age, ms, names, 16)
         return {names[i].decode(): float(ms[i]) for i in range(max(n, 0))}
 
     def set_dictionary(self, dictionary: bytes | None) -> None:

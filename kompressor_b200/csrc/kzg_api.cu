@@ -15,6 +15,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "kzg: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -(int)KZG_E_MEMORY; } } while (0)
 
 #define KZG_MAX_CHUNKS 32                 // host-pointer API: sub-batches pipelined over the copy engines
+#define KZG_EV_RING 32                   // profiled batches whose per-stage events are kept (kzg_stage_ms_history)
 #define KZG_CHUNK_BYTES (128ull << 20)   // target decoded bytes per sub-batch: big enough that a sub-batch still fills the GPU
 
 struct DevBuf {
@@ -74,8 +75,10 @@ struct kzg_ctx {
     // formatted dictionary (magic 0xEC30A437): entropy tables live behind the constants, see KzgConsts
     u32 dict_id = 0, dict_entropy = 0, dict_rep[3] = { 1, 4, 8 };
     // optional per-stage CUDA events (kzg_ctx_set_profiling)
+    // (a ring of event sets: batches enqueued back to back without a host sync in between each keep their own times)
     bool profiling = false;
-    cudaEvent_t ev[KZG_N_STAGES + 1] = {};
+    cudaEvent_t ev[KZG_EV_RING][KZG_N_STAGES + 1] = {};
+    u64 ev_seq = 0;                // profiled batches enqueued so far; the newest uses set (ev_seq - 1) % KZG_EV_RING
     bool ev_valid = false;
 };
 
@@ -179,7 +182,8 @@ extern "C" void kzg_ctx_destroy(kzg_ctx* c) {
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
     if (c->ev_tab) cudaEventDestroy(c->ev_tab);
     for (int i = 0; i < KZG_MAX_CHUNKS; i++) { if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]); if (c->ev_cmp[i]) cudaEventDestroy(c->ev_cmp[i]); }
-    for (int i = 0; i <= KZG_N_STAGES; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int r = 0; r < KZG_EV_RING; r++)
+        for (int i = 0; i <= KZG_N_STAGES; i++) if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
     delete c;
 }
 
@@ -443,7 +447,8 @@ static int enqueue_batch(kzg_ctx* c, const void* d_src, const uint64_t* d_src_of
         for (int t = 0; t < 4; t++) b.init_owner[t] = c->seg_init_owner[t];
     }
     CK(cudaMemsetAsync(c->ctr.p, 0, sizeof(KzgCounters), stream));
-    const int launches = kzg_launch_batch(b, c->sm_count, stream, c->profiling ? c->ev : nullptr);
+    const int launches = kzg_launch_batch(b, c->sm_count, stream, c->profiling ? c->ev[c->ev_seq % KZG_EV_RING] : nullptr);
+    if (c->profiling) c->ev_seq++;
     c->ev_valid = c->profiling;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_ctr + slot, c->ctr.p, sizeof(KzgCounters), cudaMemcpyDeviceToHost, stream));
@@ -497,23 +502,30 @@ extern "C" int kzg_ctx_set_profiling(kzg_ctx* c, int enable) {
     if (!c) return -(int)KZG_E_GENERIC;
     std::lock_guard<std::mutex> lock(c->mu);
     CK(cudaSetDevice(c->device));
-    if (enable && !c->ev[0])
-        for (int i = 0; i <= KZG_N_STAGES; i++) CK(cudaEventCreate(&c->ev[i]));
+    if (enable && !c->ev[0][0])
+        for (int r = 0; r < KZG_EV_RING; r++)
+            for (int i = 0; i <= KZG_N_STAGES; i++) CK(cudaEventCreate(&c->ev[r][i]));
     c->profiling = enable != 0;
     c->ev_valid = false;
+    c->ev_seq = 0;
     return 0;
 }
 
-extern "C" int kzg_last_stage_ms(kzg_ctx* c, float* ms, const char** names, int max_stages) {
-    if (!c || !ms) return -(int)KZG_E_GENERIC;
-    if (!c->ev_valid) return 0;
+extern "C" int kzg_stage_ms_history(kzg_ctx* c, int age, float* ms, const char** names, int max_stages) {
+    if (!c || !ms || age < 0) return -(int)KZG_E_GENERIC;
+    if (!c->ev_valid || (u64)age >= c->ev_seq || age >= KZG_EV_RING) return 0;
     CK(cudaSetDevice(c->device));
+    cudaEvent_t* ev = c->ev[(c->ev_seq - 1 - (u64)age) % KZG_EV_RING];
     int n = max_stages < KZG_N_STAGES ? max_stages : KZG_N_STAGES;
     for (int i = 0; i < n; i++) {
-        CK(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+        CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
         if (names) names[i] = kzg_stage_names[i];
     }
     return n;
+}
+
+extern "C" int kzg_last_stage_ms(kzg_ctx* c, float* ms, const char** names, int max_stages) {
+    return kzg_stage_ms_history(c, 0, ms, names, max_stages);
 }
 
 extern "C" int kzg_last_batch_stats(kzg_ctx* c, kzg_batch_stats* out) {
