@@ -4,9 +4,8 @@
 // A warp walks its frame's blocks in order and, inside a compressed block, the sequence records in
 // batches of 32 (one lane per sequence).  Output is assembled in a per-warp shared-memory window and
 // leaves for HBM only as 16-byte vector stores, 512 contiguous bytes per warp instruction:
-//   * the window covers output positions [T0, T0 + KZG_EX_TILE) of the current block; after every batch
-//     the completed 16-byte chunks are flushed, and when the window is full it slides, keeping the last
-//     KZG_EX_KEEP bytes as near history;
+//   * the window covers output positions [T0, T0 + KZG_EX_TILE) of the current block; when it is full its
+//     completed 16-byte chunks are flushed and it slides, keeping the last KZG_EX_KEEP bytes as near history;
 //   * every global read on the hot path is a cp.async (LDGSTS) into shared-memory staging, so no lane
 //     ever waits on a load register: the literal bytes of a batch are contiguous in the literal stream
 //     and are staged as 16-byte chunks one batch ahead; a match whose source has already left the window
@@ -28,7 +27,7 @@
 #define KZG_EX_TILE 4096u
 #endif
 #ifndef KZG_EX_KEEP
-#define KZG_EX_KEEP 1024u           // flushed history kept in the window after a slide (multiple of 16)
+#define KZG_EX_KEEP 512u            // flushed history kept in the window after a slide (multiple of 16); measured: 256 / 512 / 1024 / 1536 / 2048 -> execute 1.489 / 1.482 / 1.501 / 1.513 / 1.548 ms
 #endif
 #define KZG_EX_CAP (KZG_EX_TILE - KZG_EX_KEEP - 32u)   // most output one group of lanes may span
 #define KZG_EX_LONG 64u             // literal runs / matches longer than this are copied by the whole warp
@@ -178,6 +177,8 @@ __device__ __forceinline__ void lane_copy_or(u32 d, u32 n, u32 sa, bool fill, u3
         const u32 done = min(rem, 4u);
         A += done << 2; dd += done << 2; rem -= done;
     }
+    // (measured and dropped: advancing the addresses by whole trips and loading the carried word again after the loop
+    //  makes a trip 20 instructions instead of 24, and the kernel 17 % slower -- the reload sits on every lane's tail)
     hi = lds32(A + 4);
     red_or32(dd, __funnelshift_r(lo, hi, r) & mL);
 }
@@ -467,7 +468,8 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                 __syncwarp();
             }
             cur = ge;
-            if ((b0 & 96u) == 96u) flush(w, cur, false, lane);   // every fourth batch: ~2 KiB per flush
+            // (the window is flushed when it has to slide, ~3.5 KiB at a time; flushing every fourth or eighth batch as well
+            //  was measured: execute 1.482 / 1.490 ms against 1.472 without)
         };
 
         if (__builtin_expect(longm == 0 && (u32)(be - cur) <= KZG_EX_CAP, 1)) {
