@@ -31,8 +31,19 @@
 #endif
 #define KZG_EX_CAP (KZG_EX_TILE - KZG_EX_KEEP - 32u)   // most output one group of lanes may span
 #define KZG_EX_LONG 64u             // literal runs / matches longer than this are copied by the whole warp
+#ifndef KZG_EX_NO_LRING
+#define KZG_EX_LRING 1              // literals are staged through a ring that runs ahead of the batches (else: batch by batch)
+#endif
+#ifdef KZG_EX_LRING
+#define KZG_EX_LRING_BYTES 1024u    // the ring: four units
+#define KZG_EX_LUNIT 256u           // one unit = 16 lanes x 16 bytes, staged when the batches have come within reach of it
+#define KZG_EX_LMIRROR 96u          // the ring's first bytes once more behind its end: a run that starts before the end reads on there
+#define KZG_EX_LAHEAD (512u + KZG_EX_LMIRROR)   // staged at the start of a batch: this much from its first literal (or to the end of the literals)
+#define KZG_EX_LIT_BYTES (KZG_EX_LRING_BYTES + KZG_EX_LMIRROR)
+#else
 #define KZG_EX_LITSTAGE 1024u       // most literal bytes of one batch that are staged (else read directly)
 #define KZG_EX_LIT_BYTES (KZG_EX_LITSTAGE + 32u)
+#endif
 #define KZG_EX_MSTAGE 80u           // per-lane match staging: the 16-byte chunks covering <= 64 source bytes
 #define KZG_EX_WARP_SMEM (KZG_EX_TILE + KZG_EX_LIT_BYTES + 32u * KZG_EX_MSTAGE)
 #define KZG_EX_SMEM (KZG_EX_WARPS * KZG_EX_WARP_SMEM + 32u)      // 16 bytes of slack on either side (over-reads of lane_copy_or)
@@ -305,6 +316,24 @@ __device__ __forceinline__ void slide(Win& w, i32 cur, u32 lane) {
     if (w.Tv < nT0) w.Tv = nT0;
 }
 
+#ifdef KZG_EX_LRING
+// Literal staging through a ring.  Stream coordinate x = (lit & 15) + l for literal l, so that x = 0 is a 16-byte
+// aligned address; byte x lives at ring offset x & (KZG_EX_LRING_BYTES - 1).  Units of KZG_EX_LUNIT bytes are
+// staged (asynchronously) from `lhi` up to `target`; chunks at or beyond x_end (the end of the literals) are not read.
+// A unit at ring offset 0 is also copied behind the ring's end (its first KZG_EX_LMIRROR bytes).
+__device__ __forceinline__ u32 stage_literal_units(u32 ring, const u8* lit_base16, u32 lhi, u32 target, u32 x_end, u32 lane) {
+#pragma unroll 1
+    for (; lhi < target; lhi += KZG_EX_LUNIT) {
+        const u32 idx = lane & 15u;
+        const u32 cx = lhi + (idx << 4);
+        const bool mirror = lane >= 16u;
+        const bool p = cx < x_end && (!mirror || ((lhi & (KZG_EX_LRING_BYTES - 1u)) == 0u && idx < KZG_EX_LMIRROR / 16u));
+        const u32 dst = ring + (mirror ? KZG_EX_LRING_BYTES + (idx << 4) : (cx & (KZG_EX_LRING_BYTES - 1u)));
+        cp_async16_if(p, dst, lit_base16 + cx);
+    }
+    return lhi;
+}
+#else
 // Literal staging: the 16-byte chunks covering literal-stream bytes [l0, l1) are copied (asynchronously)
 // to `stage`; byte l of the stream then sits at stage + (l - l0) + ((lit + l0) & 15).
 // Returns false (nothing issued) if the range is too large to stage.
@@ -321,6 +350,7 @@ __device__ __forceinline__ bool stage_literals(u32 stage, const u8* lit, u32 l0,
     }
     return true;
 }
+#endif
 
 }  // namespace kzg_ex
 
@@ -356,6 +386,12 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
     u64 rec_next = lane < nseq ? seqs[lane] : 0ull;
     const u64* rec_ptr = seqs + lane;
     i32 cur = 0;
+#ifdef KZG_EX_LRING
+    // literal staging: the ring starts KZG_EX_LAHEAD bytes (whole units) ahead of the first batch
+    const u8* const lit_base16 = lit - lit_align;
+    const u32 lit_x_end = lfill ? 0u : lit_align + lit_regen;
+    u32 lhi = stage_literal_units(lstage, lit_base16, 0u, (lit_align + KZG_EX_LAHEAD + KZG_EX_LUNIT - 1u) & ~(KZG_EX_LUNIT - 1u), lit_x_end, lane);
+#else
     // literal staging of the first batch
     bool lit_staged = false;
     if (!lfill) {
@@ -363,6 +399,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
         const u32 l1 = (u32)(__shfl_sync(0xFFFFFFFFu, rec_next, nv - 1) >> 28) & 0x3FFFFu;
         lit_staged = stage_literals(lstage, lit, 0u, l1, lane);
     }
+#endif
     cp_commit();
 
     for (u32 b0 = 0; b0 < nseq; b0 += 32) {
@@ -418,8 +455,15 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
         // literal bytes of this batch were staged one batch ago: all groups but the newest are complete
         cp_wait<1>();
         __syncwarp();
+#ifdef KZG_EX_LRING
+        // every literal of the batch is staged if its last one is (staged: KZG_EX_LAHEAD from the first one, or all there are)
+        const bool this_staged = !lfill && lit_align + ((u32)(carry >> 28) & 0x3FFFFu) <= lhi;
+        const u32 lsrc = lstage + ((lit_align + p_lit_end) & (KZG_EX_LRING_BYTES - 1u));   // this lane's literals
+        (void)this_l0;
+#else
         const bool this_staged = lit_staged;
         const u32 lsrc = lstage + ((lit_align + this_l0) & 15u) - this_l0 + p_lit_end;   // this lane's literals
+#endif
         bool first_round = true;
 
         // One group of lanes (`mine`), whose output ends at block position ge and fits the window.
@@ -434,9 +478,18 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
 #endif
             if (__builtin_expect(this_staged || lfill, 1)) {
                 lane_copy_or(w.tile + (u32)((i32)p_out_end - w.T0), gll, lsrc, lfill, rle);
-            } else if (mine) {       // literal range too large to stage (rare): straight from global memory
-                const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
-                for (u32 k = 0; k < ll; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
+            } else {                 // literals beyond what is staged (rare): those runs come straight from global memory
+#ifdef KZG_EX_LRING
+                const bool st = lit_align + lit_end <= lhi;
+                lane_copy_or(w.tile + (u32)((i32)p_out_end - w.T0), st ? gll : 0u, lsrc, false, 0u);
+                __syncwarp();
+#else
+                const bool st = false;
+#endif
+                if (mine && !st) {
+                    const u32 d = w.tile + (u32)((i32)p_out_end - w.T0);
+                    for (u32 k = 0; k < ll; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
+                }
             }
             __syncwarp();
             // ---- matches, in dependency rounds
@@ -452,7 +505,34 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                 if (!pm) break;
                 const i32 fin = (i32)__shfl_sync(0xFFFFFFFFu, mdst, __ffs(pm) - 1);   // all below is final
                 const bool go = pending && need <= fin;
+#ifdef KZG_EX_COOP
+                // A round after the first usually completes one or two lanes (0.9 such rounds per batch on log text, 2.1
+                // lanes each, one lane in half of them), and the per-lane copy costs the warp ~75 instructions however few
+                // lanes take part.  One or two matches that do not overlap their own source are copied by the whole warp
+                // instead, a destination word per lane: ~20 instructions each.
+                u32 gm = 0;
+                if (!first_round) {
+                    gm = __ballot_sync(0xFFFFFFFFu, go);
+                    if (__popc(gm) > 2 || __any_sync(0xFFFFFFFFu, go && (slow || off < ml))) gm = 0;
+                }
                 if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
+                if (gm) {
+                    do {
+                        const u32 g = (u32)__ffs(gm) - 1u;
+                        gm &= gm - 1u;
+                        const u32 g_da = __shfl_sync(0xFFFFFFFFu, da, g), g_sa = __shfl_sync(0xFFFFFFFFu, sa, g), g_ml = __shfl_sync(0xFFFFFFFFu, ml, g);
+                        const u32 db = g_da & 3u, e8 = (db + g_ml) << 3;            // end of the copy in bits from the first word
+                        if ((lane << 5) < e8) {                                        // this lane's word holds bytes of the match
+                            const u32 s_ = g_sa - db + (lane << 2), A_ = s_ & ~3u;
+                            const u32 v_ = __funnelshift_r(lds32(A_), lds32(A_ + 4), (s_ & 3u) << 3);
+                            const u32 m_ = __funnelshift_lc(0xFFFFFFFFu, 0u, e8 - (lane << 5)) & (lane ? 0xFFFFFFFFu : 0xFFFFFFFFu << (db << 3));
+                            red_or32(g_da - db + (lane << 2), v_ & m_);
+                        }
+                    } while (gm);
+                } else
+#else
+                if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
+#endif
                 lane_copy_or(da, (go && !slow) ? ml : 0u, sa, false, 0u);
                 if (__builtin_expect(anyslow, 0)) {
                     __syncwarp();
@@ -600,6 +680,17 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
         // ---- stage the next batch's literals (this batch no longer reads the staging area)
         cp_wait<0>();
         __syncwarp();
+#ifdef KZG_EX_LRING
+        {   // keep the ring KZG_EX_LAHEAD ahead of the next batch's first literal, as far as the bytes still needed allow
+            // (the units below that literal's are free); usually nothing to do, a unit every fourth batch
+            const u32 x0 = lit_align + ((u32)(carry >> 28) & 0x3FFFFu);
+            const u32 target = min((x0 + KZG_EX_LAHEAD + KZG_EX_LUNIT - 1u) & ~(KZG_EX_LUNIT - 1u), (x0 & ~(KZG_EX_LUNIT - 1u)) + KZG_EX_LRING_BYTES);
+            if (__builtin_expect(lhi < target && lhi < lit_x_end && b0 + 32 < nseq, 0)) {
+                // (after a long literal run the units in between are dead already: not staged)
+                lhi = stage_literal_units(lstage, lit_base16, max(lhi, x0 & ~(KZG_EX_LUNIT - 1u)), target, lit_x_end, lane);
+            }
+        }
+#else
         lit_staged = false;
         if (!lfill && b0 + 32 < nseq) {
             const u32 nv = min(32u, nseq - b0 - 32);
@@ -607,6 +698,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
             const u32 l1 = (u32)(__shfl_sync(0xFFFFFFFFu, rec_next, nv - 1) >> 28) & 0x3FFFFu;
             if (l1 >= l0) lit_staged = stage_literals(lstage, lit, l0, l1, lane);
         }
+#endif
         cp_commit();
     }
     cp_wait<0>();
