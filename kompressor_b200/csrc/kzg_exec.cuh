@@ -31,6 +31,9 @@
 #endif
 #define KZG_EX_CAP (KZG_EX_TILE - KZG_EX_KEEP - 32u)   // most output one group of lanes may span
 #define KZG_EX_LONG 64u             // literal runs / matches longer than this are copied by the whole warp
+#ifndef KZG_EX_MEDLONG_HOT
+#define KZG_EX_MEDLONG_HOT 0        // 1: the hot variant, too, keeps a medium-long match (<= 1 KiB, short literals) inside the window (measured: execute 1.420 -> 1.429 ms on logs, 1.231 -> 1.271 on JSON)
+#endif
 #ifndef KZG_EX_NO_LRING
 #define KZG_EX_LRING 1              // literals are staged through a ring that runs ahead of the batches (else: batch by batch)
 #endif
@@ -437,20 +440,20 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
 
         // ---- matches whose source is not (entirely) inside the window any more but has been flushed: stage the
         // 16-byte chunks covering it now.  (Tv and F only grow, so the classification stays true.)
-        const bool gsrc = !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
-        u32 gsa;
-        {
+        bool gsrc = !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
+        const u32 gsa = mstage + (u32)((uintptr_t)(out + spos) & 15);
+        auto stage_sources = [&](bool want) {
             const u8* g = out + spos;
             const u32 a = (u32)((uintptr_t)g & 15);
-            const u32 nch = gsrc ? (a + ml + 15u) >> 4 : 0u;             // <= 5
+            const u32 nch = want ? (a + ml + 15u) >> 4 : 0u;             // <= 5
             g -= a;
             cp_async16_if(nch > 0, mstage, g);
             cp_async16_if(nch > 1, mstage + 16, g + 16);
             cp_async16_if(nch > 2, mstage + 32, g + 32);
             cp_async16_if(nch > 3, mstage + 48, g + 48);
             cp_async16_if(nch > 4, mstage + 64, g + 64);
-            gsa = mstage + a;
-        }
+        };
+        stage_sources(gsrc);
         cp_commit();
         // literal bytes of this batch were staged one batch ago: all groups but the newest are complete
         cp_wait<1>();
@@ -505,34 +508,9 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                 if (!pm) break;
                 const i32 fin = (i32)__shfl_sync(0xFFFFFFFFu, mdst, __ffs(pm) - 1);   // all below is final
                 const bool go = pending && need <= fin;
-#ifdef KZG_EX_COOP
-                // A round after the first usually completes one or two lanes (0.9 such rounds per batch on log text, 2.1
-                // lanes each, one lane in half of them), and the per-lane copy costs the warp ~75 instructions however few
-                // lanes take part.  One or two matches that do not overlap their own source are copied by the whole warp
-                // instead, a destination word per lane: ~20 instructions each.
-                u32 gm = 0;
-                if (!first_round) {
-                    gm = __ballot_sync(0xFFFFFFFFu, go);
-                    if (__popc(gm) > 2 || __any_sync(0xFFFFFFFFu, go && (slow || off < ml))) gm = 0;
-                }
+                // (measured and dropped: letting the whole warp copy the one or two matches a later round usually completes,
+                //  a destination word per lane -- ~20 instructions against ~75 for the per-lane pass -- made the kernel 3 % slower)
                 if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
-                if (gm) {
-                    do {
-                        const u32 g = (u32)__ffs(gm) - 1u;
-                        gm &= gm - 1u;
-                        const u32 g_da = __shfl_sync(0xFFFFFFFFu, da, g), g_sa = __shfl_sync(0xFFFFFFFFu, sa, g), g_ml = __shfl_sync(0xFFFFFFFFu, ml, g);
-                        const u32 db = g_da & 3u, e8 = (db + g_ml) << 3;            // end of the copy in bits from the first word
-                        if ((lane << 5) < e8) {                                        // this lane's word holds bytes of the match
-                            const u32 s_ = g_sa - db + (lane << 2), A_ = s_ & ~3u;
-                            const u32 v_ = __funnelshift_r(lds32(A_), lds32(A_ + 4), (s_ & 3u) << 3);
-                            const u32 m_ = __funnelshift_lc(0xFFFFFFFFu, 0u, e8 - (lane << 5)) & (lane ? 0xFFFFFFFFu : 0xFFFFFFFFu << (db << 3));
-                            red_or32(g_da - db + (lane << 2), v_ & m_);
-                        }
-                    } while (gm);
-                } else
-#else
-                if (first_round) { cp_wait<0>(); first_round = false; }     // staged match sources have landed
-#endif
                 lane_copy_or(da, (go && !slow) ? ml : 0u, sa, false, 0u);
                 if (__builtin_expect(anyslow, 0)) {
                     __syncwarp();
@@ -550,6 +528,21 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
             cur = ge;
             // (the window is flushed when it has to slide, ~3.5 KiB at a time; flushing every fourth or eighth batch as well
             //  was measured: execute 1.482 / 1.490 ms against 1.472 without)
+        };
+
+        // After the window has slid or started over in the middle of a batch (below), sources of lanes still to run may
+        // have left it: they are staged from global memory now, like the ones that had left it at the start of the batch
+        // (else those lanes copy byte by byte from L2, one dependent load per byte: measured at 5 % of the kernel's stall
+        // samples on log text, where one batch in fifty holds a long match).
+        auto restage = [&](u32 left) {
+            const bool g2 = ((left >> lane) & 1u) && !gsrc && !islong && ml > 0 && spos < w.Tv && spos + (i32)ml <= w.F && w.boff + spos >= 0;
+            if (__any_sync(0xFFFFFFFFu, g2)) {
+                stage_sources(g2);
+                cp_commit();
+                cp_wait<0>();
+                __syncwarp();
+                gsrc = gsrc || g2;
+            }
         };
 
         if (__builtin_expect(longm == 0 && (u32)(be - cur) <= KZG_EX_CAP, 1)) {
@@ -571,7 +564,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                 if (grp) {
                     const u32 lastl = 31 - __clz(grp);
                     const i32 ge = (i32)__shfl_sync(0xFFFFFFFFu, out_end, lastl);
-                    if ((u32)(ge - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); }
+                    if ((u32)(ge - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); restage(todo); }
                     run_group((grp >> lane) & 1u, ge);
                     todo &= ~grp;
                 } else {
@@ -583,9 +576,9 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                     // literals, the warp copies the match 32 bytes per step (a source at least 32 bytes behind, or disjoint).
                     {
                         const i32 sp0 = (i32)(l_poe + l_ll) - (i32)l_off;
-                        if (FULL && l_ll <= KZG_EX_LONG && (this_staged || lfill) && l_ml <= 1024u && (l_off >= 32u || l_off >= l_ml) && w.boff + sp0 >= 0) {
+                        if ((FULL || KZG_EX_MEDLONG_HOT) && l_ll <= KZG_EX_LONG && (this_staged || lfill) && l_ml <= 1024u && (l_off >= 32u || l_off >= l_ml) && w.boff + sp0 >= 0) {
                             const i32 end = (i32)(l_poe + l_ll + l_ml);
-                            if ((u32)(end - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); }
+                            if ((u32)(end - w.T0) > KZG_EX_TILE) { flush(w, cur, false, lane); slide(w, cur, lane); restage(todo & ~(1u << stop)); }
                             const bool in_win = sp0 >= w.Tv, in_glob = sp0 + (i32)l_ml <= w.F;
                             if ((u32)(end - w.T0) <= KZG_EX_TILE && (in_win || in_glob)) {
                                 lane_copy_or(w.tile + (u32)((i32)l_poe - w.T0), lane == stop ? ll : 0u, lsrc, lfill, rle);
@@ -673,6 +666,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
                     zero_window(w.tile, 0u, KZG_EX_TILE, lane);     // the window starts over, empty
                     __syncwarp();
                     todo &= ~(1u << stop);
+                    restage(todo);
                 }
             }
         }
