@@ -24,10 +24,10 @@
 
 #define KZG_EX_WARPS 4
 #ifndef KZG_EX_TILE
-#define KZG_EX_TILE 4096u
+#define KZG_EX_TILE 3264u            // with the staging areas: 8 CTAs of 4 warps per SM (measured, CTAs x tile: 7 x 4096 -> 1.308 ms, 8 x 3264 -> 1.275, 9 x 2496 -> 1.82, 10 x 1856 -> 1.91: registers spill below 64)
 #endif
 #ifndef KZG_EX_KEEP
-#define KZG_EX_KEEP 512u            // flushed history kept in the window after a slide (multiple of 16); measured: 256 / 512 / 1024 / 1536 / 2048 -> execute 1.489 / 1.482 / 1.501 / 1.513 / 1.548 ms
+#define KZG_EX_KEEP 384u            // flushed history kept in the window after a slide (multiple of 16); measured with the 4 KiB window: 256 / 512 / 1024 / 1536 / 2048 -> execute 1.489 / 1.482 / 1.501 / 1.513 / 1.548 ms
 #endif
 #define KZG_EX_CAP (KZG_EX_TILE - KZG_EX_KEEP - 32u)   // most output one group of lanes may span
 #define KZG_EX_LONG 64u             // literal runs / matches longer than this are copied by the whole warp
@@ -720,7 +720,7 @@ __device__ __forceinline__ u32 kzg_exec_sequences(const KzgBatch& B, const KzgBl
 #define KZG_EX_BIG_FRAME_BLOCKS 8u
 template <bool FULL>
 #ifndef KZG_EX_MINBLOCKS
-#define KZG_EX_MINBLOCKS 7
+#define KZG_EX_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(KZG_EX_WARPS * 32, KZG_EX_MINBLOCKS) kzg_exec_kernel(KzgBatch B) {
     using namespace kzg_ex;
