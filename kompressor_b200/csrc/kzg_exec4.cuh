@@ -1,13 +1,13 @@
-// Execute stage (s5, ZSTD_execSequence) for sm_100a, CTA-per-frame variant: sixteen warps share ONE frame.
+// Execute stage (s5, ZSTD_execSequence) for sm_100a, CTA-per-frame variant: thirty-two warps share ONE frame.
 //
 // The warp-per-frame kernel (kzg_exec.cuh) needs thousands of frames in flight; a batch of sixteen 4 MiB frames
 // (BASELINE configs[4]: level 19, 8 MiB window) or a single frame behind the streaming shim leaves the GPU idle while
-// one warp walks 140 000 sequences.  Here a CTA takes a frame, and inside a block it executes 512 sequences per step,
+// one warp walks 140 000 sequences.  Here a CTA takes a frame, and inside a block it executes 1 024 sequences per step,
 // one lane per sequence:
 //   * the window is the WHOLE block (128 KiB + alignment) in shared memory: every match source inside the block is
 //     shared -> shared, nothing slides, and the block leaves as one coalesced 16-byte-vector flush;
 //   * sources before the block (earlier blocks of the frame, the dictionary) are read from global memory / L2 by the
-//     lane itself -- with sixteen warps per SM the load latency is covered by the other warps; at level 19 these are
+//     lane itself -- with thirty-two warps per SM the load latency is covered by the other warps; at level 19 these are
 //     the majority (median distance 120 KB) and have no dependencies inside the step;
 //   * the literals of a step are contiguous in the literal stream: the CTA stages them with 16-byte loads, lanes copy
 //     them shared -> shared;
@@ -28,10 +28,14 @@
 #include <stdio.h>
 #endif
 
-#define KZG_X4_WARPS 16
+#ifndef KZG_X4_WARPS
+#define KZG_X4_WARPS 32                                 // measured on 16 / 64 level-19 frames of 4 MiB: 8 warps 7.0 / 7.3 ms, 12: 5.8 / 6.1, 16: 5.1 / 5.5, 20: 4.7 / 5.0, 24: 4.5 / 4.8, 32: 4.3 / 4.6
+#endif
 #define KZG_X4_THREADS (KZG_X4_WARPS * 32)
 #define KZG_X4_WIN (KZG_BLOCK_MAX + 48u)                // the block + alignment + the words lane copies may read past an end
-#define KZG_X4_LITCAP 32768u                            // most literal bytes of one step that are staged
+#ifndef KZG_X4_LITCAP
+#define KZG_X4_LITCAP 12288u                            // most literal bytes of one step that are staged (with 32 warps the per-lane match staging takes 80 KB)
+#endif
 #define KZG_X4_LIT_BYTES (KZG_X4_LITCAP + 48u)
 #define KZG_X4_MISC 256u                                // first-pending positions (2 x 16), literal range, flags
 #define KZG_X4_MSTAGE 80u                               // per-lane staging of a match source read from global memory (<= 64 bytes)
@@ -180,18 +184,21 @@ __device__ __forceinline__ u32 kzg_exec4_block(const KzgBatch& B, const KzgBlock
 
         // ---- literals of this step: staged by the CTA, then one lane per run
         const u32 l0 = misc[32], l1 = misc[33];
-        const bool staged = !lfill && l1 - l0 <= KZG_X4_LITCAP;
+        // (a step with more literals than the staging area holds stages the first KZG_X4_LITCAP bytes; the runs beyond come
+        //  straight from global memory)
+        const u32 l1s = min(l1, l0 + KZG_X4_LITCAP);
+        const bool staged = !lfill && l1 >= l0;
         const u32 la = (u32)((uintptr_t)(lit + l0) & 15);
         if (staged) {
             const uint4* g4 = reinterpret_cast<const uint4*>(lit + l0 - la);
-            const u32 nch = (la + (l1 - l0) + 15u) >> 4;
+            const u32 nch = (la + (l1s - l0) + 15u) >> 4;
             for (u32 c = tid; c < nch; c += KZG_X4_THREADS) sts128(lstage + (c << 4), __ldg(g4 + c));
         }
         __syncthreads();
         {
             const u32 d = win + p_out_end;
             const u32 n = ll < KZG_X4_COOP ? ll : 0u;
-            if (lfill || staged) lane_copy(d, n, lstage + la + (p_lit_end - l0), lfill, rle);
+            if (lfill || (staged && lit_end <= l1s)) lane_copy(d, n, lstage + la + (p_lit_end - l0), lfill, rle);
             else for (u32 k = 0; k < n; k++) sts8(d + k, (u32)__ldg(lit + p_lit_end + k));
             u32 longl = __ballot_sync(0xFFFFFFFFu, ll >= KZG_X4_COOP);
             while (longl) {

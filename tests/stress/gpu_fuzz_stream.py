@@ -68,6 +68,10 @@ for case in range(n):
                 oracle.made_up_literals()
                 o_err = oracle.decompress(fr, 4 << 20)[1]
                 divergent = divergent or oracle.made_up_literals() or (o_err, z.decompress_oneshot(fr, 4 << 20)[1]) == (20, 70)
+                # the same kind seen only by the streaming decoder: with an output slice below the frame's content size libzstd
+                # decodes a corrupt block into its own window-sized buffer and runs out of room (70) before it sees the
+                # corruption the one-shot decoder -- and the oracle, and this decoder -- report (20)
+                divergent = divergent or (o_err, ref[1], got[1]) == (20, 70, 20)
         if mode >= 0.3 and divergent and got[1] in (20, 22) and got[0] == ref[0][:len(got[0])]:
             known += 1
         else:
