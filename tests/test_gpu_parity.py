@@ -272,3 +272,60 @@ def test_configs4_exact_shape(dec, libzstd):
     outs, status, sizes = run(dec, frames, [4 << 20] * 2)
     assert (status == 0).all() and (sizes == 4 << 20).all()
     assert hashlib.sha256(b"".join(outs)).digest() == hashlib.sha256(c.raw.tobytes()).digest()
+
+
+def test_first_design_window_paths(dec, libzstd, monkeypatch):
+    """The warp-per-frame execute kernel (kzg_exec.cuh, the batch path) on inputs made for the paths of its shared-memory
+    window -- small batches normally go to the CTA-per-frame kernel, KZG_EXEC_CTA_BELOW=0 sends them here:
+    literal runs of 17 .. 64 bytes (the copy loop instead of the straight-line placement), of more than 64 and more
+    than 512 bytes (warp-wide copies, the literal ring skipping ahead), long matches in the middle of a batch (the
+    window starts over and the sources of the remaining lanes are staged again), short periods, sources right at the
+    window's lower edge, and frames of up to eight blocks."""
+    import corpus
+    monkeypatch.setenv("KZG_EXEC_CTA_BELOW", "0")
+    rng = np.random.default_rng(17)
+    text = bytes(corpus.generate("logs", 123, 400000))
+    js = bytes(corpus.generate("json", 321, 200000))
+
+    def noise(n):
+        return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+
+    raws = []
+    # literal runs of every length class between short matches
+    for lo, hi in ((1, 16), (17, 64), (65, 300), (400, 2000), (1, 3000)):
+        parts, pos = [], 0
+        while sum(map(len, parts)) < 120000:
+            parts.append(noise(int(rng.integers(lo, hi + 1))))
+            n = int(rng.integers(4, 40))
+            parts.append(text[pos:pos + n]); pos = (pos + 977) % 300000
+        raws.append(b"".join(parts))
+    # long matches (65 .. 5000 bytes) from near and far in the middle of ordinary text
+    for span in (3000, 60000):
+        parts, pos = [text[:span]], span
+        while sum(map(len, parts)) < 200000:
+            parts.append(text[pos:pos + int(rng.integers(20, 400))]); pos += 400
+            back = int(rng.integers(100, span))
+            hist = b"".join(parts)
+            parts.append(hist[-back:][:int(rng.integers(65, 5000))])
+        raws.append(b"".join(parts))
+    # short periods and runs between text, sources a few hundred bytes back (the window's lower edge after a slide)
+    parts = []
+    for i in range(400):
+        parts.append(text[i * 300:i * 300 + int(rng.integers(30, 200))])
+        parts.append(bytes([65 + i % 7]) * int(rng.integers(1, 90)))
+        parts.append((b"xy", b"abc", b"12345", b"abcdefg")[i % 4] * int(rng.integers(1, 30)))
+    raws.append(b"".join(parts))
+    raws.append(b"".join(text[i:i + 37] + text[max(0, i - 390):max(0, i - 390) + 21] + text[max(0, i - 3200):max(0, i - 3200) + 33]
+                         for i in range(4000, 160000, 180)))
+    # plain corpora in single-block and multi-block frames (at most eight blocks stay with this kernel)
+    raws += [text[:65536], js[:65536], text[:131072 * 3 + 17], (js + text)[:131072 * 8], bytes(corpus.generate("mixed", 5, 500000))]
+    frames, caps, expect = [], [], []
+    for i, r in enumerate(raws):
+        for lvl in (1, 3, 9, 19):
+            frames.append(libzstd.compress(r, lvl, checksum=bool(i & 1), pledged=bool(lvl & 1)))
+            caps.append(len(r) + (i % 3))
+            expect.append(r)
+    outs, status, _ = run(dec, frames, caps)
+    assert (status == 0).all(), status
+    for k, (o, e) in enumerate(zip(outs, expect)):
+        assert o == e, k
