@@ -49,6 +49,7 @@
 #define KZG_FSE_PAIR_SMEM (KZG_FSE_TAB_BYTES + KZG_FSE_RING_BYTES + KZG_FSE_Q_BYTES + KZG_FSE_MISC_BYTES)
 #define KZG_FSE_CODE_WORDS 192                              // 36 LL + 53 ML packed code entries, padded to 128 words; then (from byte 512,
                                                             // aligned to 64) the extra-bit counts alone, one BYTE per code: 64 B LL, 64 B ML
+#define KZG_FSE_ALIGN_SLACK 128                             // the kernel aligns its area to 128 bytes itself
 #define KZG_FSE_SMEM (KZG_FSE_CODE_WORDS * 4 + KZG_FSE_PAIRS * KZG_FSE_PAIR_SMEM)
 // Up to three more warps ride along in every CTA and decode Huffman literals (kzg_huf_warp_loop) in the shared memory
 // and the issue slots the four sequence warps leave free -- where they can finish all of them meanwhile (see the kernel).
@@ -57,7 +58,7 @@
 #define KZG_FSE_LIT_WARPS_MAX 3
 #define KZG_FSE_THREADS_OF(nlit) (KZG_FSE_WARPS * 32 + 64 * (nlit))
 #define KZG_FSE_THREADS KZG_FSE_THREADS_OF(KZG_FSE_LIT_WARPS_MAX)
-#define KZG_FSE_SMEM_TOTAL_OF(nlit) (KZG_FSE_SMEM + (nlit) * KZG_HUF_WARP_SMEM)
+#define KZG_FSE_SMEM_TOTAL_OF(nlit) (KZG_FSE_ALIGN_SLACK + KZG_FSE_SMEM + (nlit) * KZG_HUF_WARP_SMEM)
 #define KZG_FSE_SMEM_TOTAL KZG_FSE_SMEM_TOTAL_OF(KZG_FSE_LIT_WARPS_MAX)
 #define KZG_FSE_DONE_WORD 127                               // in the code-word area: pairs of this CTA that have finished
 #define KZG_FSE_SEQ_CYCLES 200ull                           // one sequence of the chain, in SM clocks (measured: 195 alone, 211 with riders)
@@ -193,7 +194,10 @@ __device__ __noinline__ void slow_decode(const Job& j, u32 tLL, u32 tML, u32 tOF
 //   hi:lo  64-bit window at the sequence's bit position        eLL / eML  the LL / ML table cells (code in bits 0-5)
 __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B) {
     using namespace kzg_fse;
-    extern __shared__ uint4 smem4[];
+    extern __shared__ uint4 smem4_raw[];
+    // the area starts on a 128-byte boundary (KZG_FSE_ALIGN_SLACK bytes are allocated for that): a lane's 128-byte ring is
+    // then aligned, and a ring address is one LOP3 -- (offset & 0x7C) | ring -- instead of an AND and an add
+    uint4* const smem4 = reinterpret_cast<uint4*>(reinterpret_cast<u8*>(smem4_raw) + ((0u - smem_addr(smem4_raw)) & 127u));
     u32* llx = reinterpret_cast<u32*>(smem4);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 pair = warp >> 1;
@@ -320,9 +324,9 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
 #define KZG_FSE_WINDOW(hi, lo)                                                     \
         {                                                                          \
             const u32 t_ = (u32)(P >> 3), q_ = (u32)P & 31u;                       \
-            const u32 w2_ = lds32(s_ring + (t_ & 0x7Cu));                          \
-            const u32 w1_ = lds32(s_ring + ((t_ - 4u) & 0x7Cu));                   \
-            const u32 w0_ = lds32(s_ring + ((t_ - 8u) & 0x7Cu));                   \
+            const u32 w2_ = lds32(s_ring | (t_ & 0x7Cu));                          \
+            const u32 w1_ = lds32(s_ring | ((t_ - 4u) & 0x7Cu));                   \
+            const u32 w0_ = lds32(s_ring | ((t_ - 8u) & 0x7Cu));                   \
             hi = __funnelshift_r(w1_, w2_, q_);                                    \
             lo = __funnelshift_r(w0_, w1_, q_);                                    \
         }
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
         if (chain) {
             // =================================================================== chain warp
             const u32 szLL = 1u << j.logLL, szOF = 1u << j.logOF, szML = 1u << j.logML;
-            const u32 kLL = j.logLL - 31u, kOF = j.logOF - 31u, kML = j.logML - 31u;   // nbBits = k + clz(next)
+            const u32 kLL = j.logLL - 25u, kOF = j.logOF - 25u, kML = j.logML - 25u;   // nbBits = k + clz(cell): a cell is next << 6 | symbol, next >= 1
             bool wide = false;                   // a sequence with more than 32 extra bits was seen
             // The loop is one dependency chain per sequence (cell -> extra-bit counts -> E -> state bits -> next cell),
             // and every dependent instruction on it costs a lone warp ~12 clocks, a shared-memory load ~32.  So the chain
@@ -422,9 +426,9 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
 #else
                     const u32 llb = lds8(s_llb | (eLL & 63u)), mlb = lds8(s_mlb | (eML & 63u));
 #endif
-                    const u32 nLL = eLL >> 6, nML = eML >> 6, nOF = eOF >> 6;
-                    // nbBits = log - floor(log2(next)) = log - 31 + clz(next)
-                    const u32 bLL = (u32)__clz((int)nLL) + kLL, bML = (u32)__clz((int)nML) + kML, bOF = (u32)__clz((int)nOF) + kOF;
+                    // nbBits = log - floor(log2(next)) = log - 25 + clz(cell); next << 6 = the cell without its symbol
+                    const u32 mLL = eLL & 0xFFC0u, mML = eML & 0xFFC0u, mOF = eOF & 0xFFC0u;
+                    const u32 bLL = (u32)__clz((int)eLL) + kLL, bML = (u32)__clz((int)eML) + kML, bOF = (u32)__clz((int)eOF) + kOF;
                     const u32 E = ofc + mlb + llb;
                     wide |= act && E > KZG_FSE_WIDE_LIMIT;
 #ifndef DBG_NOQ
@@ -433,9 +437,9 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
                     // state bits sit right below the E extra bits (valid when E <= 32: E + 26 <= 58 bits)
                     const u32 X = __funnelshift_lc(lo, hi, E);
                     const u32 X2 = X << bLL, X3 = X2 << bML;
-                    aLL = zLL + (nLL << (bLL + 6u)) + (__funnelshift_lc(X, 0u, bLL) << 6);
-                    aML = zML + (nML << (bML + 6u)) + (__funnelshift_lc(X2, 0u, bML) << 6);
-                    aOF = zOF + (nOF << (bOF + 6u)) + (__funnelshift_lc(X3, 0u, bOF) << 6);
+                    aLL = zLL + (mLL << bLL) + (__funnelshift_lc(X, 0u, bLL) << 6);
+                    aML = zML + (mML << bML) + (__funnelshift_lc(X2, 0u, bML) << 6);
+                    aOF = zOF + (mOF << bOF) + (__funnelshift_lc(X3, 0u, bOF) << 6);
                     P -= (i32)(act ? E + (notlast ? bLL + bML + bOF : 0u) : 0u);
                 }
                 }
