@@ -212,6 +212,21 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
     }
     __syncthreads();
     if (warp >= KZG_FSE_WARPS && !(warp & 1u)) return;
+    const long long t_start = clock64();
+    // Whether literal warps ride in this launch, and until when they take new tickets (0: they do not ride); see below.
+    auto ride_deadline = [&]() -> long long {
+        const u64 nsb = B.ctr->n_sblocks, nhb = B.ctr->n_hblocks, nsq = B.ctr->seq_used;
+        if (nsb == 0 || nhb == 0 || nsq < nsb * 1024u || B.lit_ride == 2u) return 0;
+        const u64 lanes = (u64)gridDim.x * (KZG_FSE_PAIRS * 32u);
+        const u64 est_seq = ((nsb + lanes - 1) / lanes) * (nsq / nsb);
+        const u64 riders = (u64)gridDim.x * ((blockDim.x - KZG_FSE_WARPS * 32u) / 64u);
+        const u64 est_tkt = (B.ctr->lit_used / nhb / 4u) * 3u / 4u;                 // one ticket: the streams of 8 blocks side by side
+        // tickets the riders can finish before the sequence stage ends, against all of them: at least four fifths, or none
+        // (measured: riders that take 87 % leave kzg_huf_kernel a shorter, emptier launch and win 2-5 %; 45 % loses 2 %)
+        const u64 fit = est_tkt ? est_seq / est_tkt : 0xFFFFull;
+        if (B.lit_ride == 0u && fit * riders * 5u < ((nhb + 7) / 8) * 4u) return 0;
+        return t_start + (long long)((est_seq > est_tkt ? est_seq - est_tkt : 0ull) * KZG_FSE_SEQ_CYCLES) + 1;
+    };
     if (warp > KZG_FSE_WARPS) {                             // a literal warp
         // Both stages are serial chains, so the riders are all or nothing: whatever they leave takes kzg_huf_kernel one
         // full chain however little it is, and riders cost the sequence warps ~7 % (shared-memory traffic).  Measured on
@@ -221,18 +236,8 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
         // from the batch's counters in units of one sequence of the chain (KZG_FSE_SEQ_CYCLES; a rider's literal symbol
         // takes ~3/4 of that), and no rider takes a new ticket it could not finish by then (clock64 deadline; every SM
         // starts its one CTA at the same time).  Riders on SMs whose pairs have no block ride too.
-        const u64 nsb = B.ctr->n_sblocks, nhb = B.ctr->n_hblocks, nsq = B.ctr->seq_used;
-        if (nsb == 0 || nhb == 0 || nsq < nsb * 1024u || B.lit_ride == 2u) return;
-        const long long t0 = clock64();
-        const u64 lanes = (u64)gridDim.x * (KZG_FSE_PAIRS * 32u);
-        const u64 est_seq = ((nsb + lanes - 1) / lanes) * (nsq / nsb);
-        const u64 riders = (u64)gridDim.x * ((blockDim.x - KZG_FSE_WARPS * 32u) / 64u);
-        const u64 est_tkt = (B.ctr->lit_used / nhb / 4u) * 3u / 4u;                 // one ticket: the streams of 8 blocks side by side
-        // tickets the riders can finish before the sequence stage ends, against all of them: at least four fifths, or none
-        // (measured: riders that take 87 % leave kzg_huf_kernel a shorter, emptier launch and win 2-5 %; 45 % loses 2 %)
-        const u64 fit = est_tkt ? est_seq / est_tkt : 0xFFFFull;
-        if (B.lit_ride == 0u && fit * riders * 5u < ((nhb + 7) / 8) * 4u) return;
-        const long long deadline = t0 + (long long)((est_seq > est_tkt ? est_seq - est_tkt : 0ull) * KZG_FSE_SEQ_CYCLES) + 1;
+        const long long deadline = ride_deadline();
+        if (!deadline) return;
         kzg_huf_warp_loop<KZG_HUF_L1_BITS, KZG_HUF_L2CAP, false>(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_SMEM + ((warp - KZG_FSE_WARPS - 1u) >> 1) * KZG_HUF_WARP_SMEM, lane, deadline, 0xFFFFFFFFu);
         return;
     }
@@ -529,4 +534,13 @@ __global__ void __launch_bounds__(KZG_FSE_THREADS, 1) kzg_fse_kernel(KzgBatch B)
 #undef KZG_FSE_WINDOW
         bar_sync(BAR_PAIR);          // queue, ring, tables and hand-over words are free for the next round
     }
+#ifndef KZG_FSE_NO_PAIR_RIDE
+    // A pair that finds no sequence work left -- 16 384 blocks on 9 472 block slots leave a quarter of the pairs idle in the
+    // second wave -- decodes literals too, each of its warps in a piece of the pair's own table area.  (The literal warps
+    // were what the launch waited for on log text: ~4.6 tickets per literal warp run as five.)
+    {
+        const long long deadline = ride_deadline();
+        if (deadline) kzg_huf_warp_loop<KZG_HUF_L1_BITS, KZG_HUF_L2CAP, false>(B, reinterpret_cast<u8*>(smem4) + KZG_FSE_CODE_WORDS * 4 + pair * KZG_FSE_PAIR_SMEM + (warp & 1u) * KZG_HUF_WARP_SMEM, lane, deadline, 0xFFFFFFFFu);
+    }
+#endif
 }
