@@ -93,7 +93,10 @@ __device__ __forceinline__ void build(WarpScratch& sc, const KzgFseDesc* d, u32 
 
 }  // namespace kzg_tab
 
-__global__ void __launch_bounds__(KZG_TAB_WARPS * 32) kzg_fsetab_kernel(KzgBatch B) {
+#ifndef KZG_TAB_MINBLOCKS
+#define KZG_TAB_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(KZG_TAB_WARPS * 32, KZG_TAB_MINBLOCKS) kzg_fsetab_kernel(KzgBatch B) {
     using namespace kzg_tab;
     __shared__ WarpScratch scratch[KZG_TAB_WARPS];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

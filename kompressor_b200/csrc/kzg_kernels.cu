@@ -291,7 +291,10 @@ int kzg_launch_batch(const KzgBatch& b_in, int sm_count, cudaStream_t stream, cu
     KZG_MARK();
     kzg_link_kernel<<<fgrid, 128, 0, stream>>>(b);
     KZG_MARK();
-    kzg_fsetab_kernel<<<sm_count * 8, KZG_TAB_WARPS * 32, 0, stream>>>(b);
+#ifndef KZG_TAB_GRID_PER_SM
+#define KZG_TAB_GRID_PER_SM 8
+#endif
+    kzg_fsetab_kernel<<<sm_count * KZG_TAB_GRID_PER_SM, KZG_TAB_WARPS * 32, 0, stream>>>(b);
     KZG_MARK();
     kzg_fse_kernel<<<sm_count, KZG_FSE_THREADS_OF(nlit), fse_smem, stream>>>(b);          // sequences, and literals on the side
     KZG_MARK();
