@@ -61,7 +61,9 @@
 #define KZG_FSE_SMEM_TOTAL_OF(nlit) (KZG_FSE_ALIGN_SLACK + KZG_FSE_SMEM + (nlit) * KZG_HUF_WARP_SMEM)
 #define KZG_FSE_SMEM_TOTAL KZG_FSE_SMEM_TOTAL_OF(KZG_FSE_LIT_WARPS_MAX)
 #define KZG_FSE_DONE_WORD 127                               // in the code-word area: pairs of this CTA that have finished
-#define KZG_FSE_SEQ_CYCLES 200ull                           // one sequence of the chain, in SM clocks (measured: 195 alone, 211 with riders)
+#ifndef KZG_FSE_SEQ_CYCLES
+#define KZG_FSE_SEQ_CYCLES 200ull                           // one sequence of the chain, in SM clocks (measured: 175 alone, 190 with riders; 170 .. 220 give the same times on log text: the literal warps are done before any of these deadlines)
+#endif
 #ifndef KZG_FSE_WIDE_LIMIT
 #define KZG_FSE_WIDE_LIMIT 32u                              // most extra bits per sequence the fast loop extracts (tests lower it)
 #endif
